@@ -1,0 +1,290 @@
+// 255-bit Montgomery field arithmetic on 8 x 32-bit limbs for the Pallas/Vesta cycle (K1 of
+// SURVEY.md 2b).  Replaces ark-ff 0.2 `Fp256<P>` (4 x u64 Montgomery, R = 2^256) on the device: the
+// memory image is identical (little-endian limbs), so field elements cross the C-ABI untouched.
+//
+// Both moduli are 2^254 + t with limbs [1, m1, m2, m3, 0, 0, 0, 2^30] and -m^{-1} mod 2^32 = -1
+// (SURVEY.md App. B): the Montgomery quotient digit is a negation and each reduction round needs
+// three real limb products.
+//
+// Carry chains are written as one PTX instruction per `asm volatile` statement (add.cc / madc.*),
+// which ptxas fuses into IMAD.WIDE + IADD3.X; the same source compiles for the host with an emulated
+// carry flag so tests can check the arithmetic without a GPU (tests/host/…).
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ACC_HD __host__ __device__ __forceinline__
+#define ACC_D __device__ __forceinline__
+#else
+#define ACC_HD inline
+#define ACC_D inline
+#endif
+
+namespace accmsm {
+
+// ---------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define ACC_ASM_R1(name, ptx)                                                       \
+    ACC_D uint32_t name(uint32_t a, uint32_t b) {                                   \
+        uint32_t r;                                                                 \
+        asm volatile(ptx " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));                \
+        return r;                                                                   \
+    }
+#define ACC_ASM_R3(name, ptx)                                                       \
+    ACC_D uint32_t name(uint32_t a, uint32_t b, uint32_t c) {                       \
+        uint32_t r;                                                                 \
+        asm volatile(ptx " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));    \
+        return r;                                                                   \
+    }
+ACC_ASM_R1(add_cc, "add.cc.u32")
+ACC_ASM_R1(addc_cc, "addc.cc.u32")
+ACC_ASM_R1(addc, "addc.u32")
+ACC_ASM_R1(sub_cc, "sub.cc.u32")
+ACC_ASM_R1(subc_cc, "subc.cc.u32")
+ACC_ASM_R1(subc, "subc.u32")
+ACC_ASM_R3(mad_lo_cc, "mad.lo.cc.u32")
+ACC_ASM_R3(madc_lo_cc, "madc.lo.cc.u32")
+ACC_ASM_R3(mad_hi_cc, "mad.hi.cc.u32")
+ACC_ASM_R3(madc_hi_cc, "madc.hi.cc.u32")
+ACC_ASM_R3(madc_hi, "madc.hi.u32")
+ACC_ASM_R3(madc_lo, "madc.lo.u32")
+ACC_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+ACC_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// 64-bit (register-pair) forms: `mul.wide.u32` feeding `add.cc.u64` is fused by ptxas into a single
+// IMAD.WIDE.U32(.X) with carry-in/out predicates; keeping the accumulators as 64-bit virtual registers
+// makes the pair alignment explicit, which is what lets the whole multiplier stay on wide IMADs.
+ACC_D uint64_t mulw(uint32_t a, uint32_t b) { uint64_t r; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
+ACC_D uint64_t add_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("add.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+ACC_D uint64_t addc_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+ACC_D uint64_t addc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+ACC_D uint32_t lo32(uint64_t a) { uint32_t l, h; asm("mov.b64 {%0, %1}, %2;" : "=r"(l), "=r"(h) : "l"(a)); return l; }
+ACC_D uint32_t hi32(uint64_t a) { uint32_t l, h; asm("mov.b64 {%0, %1}, %2;" : "=r"(l), "=r"(h) : "l"(a)); return h; }
+ACC_D uint64_t pack64(uint32_t l, uint32_t h) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(l), "r"(h)); return r; }
+#undef ACC_ASM_R1
+#undef ACC_ASM_R3
+#else
+// Host emulation (unit tests only): one carry/borrow flag per thread, PTX semantics.
+namespace hostcc { static thread_local uint32_t cf = 0; }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; hostcc::cf = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + hostcc::cf; hostcc::cf = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + hostcc::cf; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b; hostcc::cf = (uint32_t)(d >> 63); return (uint32_t)d; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b - hostcc::cf; hostcc::cf = (uint32_t)(d >> 63); return (uint32_t)d; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - hostcc::cf; }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint64_t mulw(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
+inline uint64_t add_cc64(uint64_t a, uint64_t b) { unsigned __int128 s = (unsigned __int128)a + b; hostcc::cf = (uint32_t)(s >> 64); return (uint64_t)s; }
+inline uint64_t addc_cc64(uint64_t a, uint64_t b) { unsigned __int128 s = (unsigned __int128)a + b + hostcc::cf; hostcc::cf = (uint32_t)(s >> 64); return (uint64_t)s; }
+inline uint64_t addc64(uint64_t a, uint64_t b) { return a + b + hostcc::cf; }
+inline uint32_t lo32(uint64_t a) { return (uint32_t)a; }
+inline uint32_t hi32(uint64_t a) { return (uint32_t)(a >> 32); }
+inline uint64_t pack64(uint32_t l, uint32_t h) { return ((uint64_t)h << 32) | l; }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_lo(a, b), c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_lo(a, b), c); }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_hi(a, b), c); }
+inline uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_lo(a, b), c); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// field parameters. FIELD 0 = Fp (Pallas base / Vesta scalar), FIELD 1 = Fq (Pallas scalar / Vesta base)
+// ---------------------------------------------------------------------------------------------
+template <int FIELD> struct FieldParams;
+template <> struct FieldParams<0> {
+    static constexpr uint32_t M1 = 0x992d30edu, M2 = 0x094cf91bu, M3 = 0x224698fcu;
+    static constexpr uint32_t R[8] = {0xfffffffdu, 0x34786d38u, 0xe41914adu, 0x992c350bu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
+    static constexpr uint32_t R2[8] = {0x0000000fu, 0x8c78ecb3u, 0x8b0de0e7u, 0xd7d30dbdu, 0xc3c95d18u, 0x7797a99bu, 0x7b9cb714u, 0x096d41afu};
+};
+template <> struct FieldParams<1> {
+    static constexpr uint32_t M1 = 0x8c46eb21u, M2 = 0x0994a8ddu, M3 = 0x224698fcu;
+    static constexpr uint32_t R[8] = {0xfffffffdu, 0x5b2b3e9cu, 0xe3420567u, 0x992c350bu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
+    static constexpr uint32_t R2[8] = {0x0000000fu, 0xfc9678ffu, 0x891a16e3u, 0x67bb433du, 0x04ccf590u, 0x7fae2310u, 0x7ccfdaa9u, 0x096d41afu};
+};
+constexpr uint32_t MOD_L0 = 1u, MOD_L7 = 0x40000000u;
+
+// A zero the compiler cannot fold (constant bank, never written): multiplying by it turns a two-limb
+// carry ripple into one IMAD.WIDE.U32.X on the multiplier pipe instead of two IADD3.X on the ALU pipe.
+// ACC_MUL_WIDE_RIPPLES picks how many of the 3 ripples per reduction round take that route, to balance
+// the two half-rate pipes (tools/powerprobe.cu measures both at 2 clk per warp instruction per SMSP).
+#if defined(__CUDACC__)
+static __constant__ uint32_t ACC_OPAQUE_ZERO;
+#endif
+#ifndef ACC_MUL_WIDE_RIPPLES
+#define ACC_MUL_WIDE_RIPPLES 0
+#endif
+ACC_HD uint32_t opaque_zero() {
+#if defined(__CUDA_ARCH__)
+    return ACC_OPAQUE_ZERO;
+#else
+    return 0u;
+#endif
+}
+
+// A field element in registers: 8 little-endian 32-bit limbs, Montgomery form, canonical (< m).
+struct alignas(16) fe_t {
+    uint32_t l[8];
+};
+
+template <int FIELD> struct Fp {
+    using P = FieldParams<FIELD>;
+
+    static ACC_HD uint32_t mod_limb(int i) {
+        return i == 0 ? MOD_L0 : i == 1 ? P::M1 : i == 2 ? P::M2 : i == 3 ? P::M3 : i == 7 ? MOD_L7 : 0u;
+    }
+    static ACC_HD fe_t zero() { fe_t r; for (int i = 0; i < 8; i++) r.l[i] = 0; return r; }
+    static ACC_HD fe_t one() {
+        fe_t r;
+        r.l[0] = 0xfffffffdu; r.l[1] = FIELD == 0 ? 0x34786d38u : 0x5b2b3e9cu;
+        r.l[2] = FIELD == 0 ? 0xe41914adu : 0xe3420567u; r.l[3] = 0x992c350bu;
+        r.l[4] = r.l[5] = r.l[6] = 0xffffffffu; r.l[7] = 0x3fffffffu;
+        return r;
+    }
+    static ACC_HD fe_t r2() {
+        fe_t r;
+        if (FIELD == 0) {
+            r.l[0] = 0x0000000fu; r.l[1] = 0x8c78ecb3u; r.l[2] = 0x8b0de0e7u; r.l[3] = 0xd7d30dbdu;
+            r.l[4] = 0xc3c95d18u; r.l[5] = 0x7797a99bu; r.l[6] = 0x7b9cb714u; r.l[7] = 0x096d41afu;
+        } else {
+            r.l[0] = 0x0000000fu; r.l[1] = 0xfc9678ffu; r.l[2] = 0x891a16e3u; r.l[3] = 0x67bb433du;
+            r.l[4] = 0x04ccf590u; r.l[5] = 0x7fae2310u; r.l[6] = 0x7ccfdaa9u; r.l[7] = 0x096d41afu;
+        }
+        return r;
+    }
+    static ACC_HD bool is_zero(const fe_t &a) {
+        return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0;
+    }
+    static ACC_HD bool eq(const fe_t &a, const fe_t &b) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d |= a.l[i] ^ b.l[i];
+        return d == 0;
+    }
+
+    // r = a - m if a >= m else a   (a < 2m)
+    static ACC_HD void reduce_once(fe_t &a) {
+        uint32_t u[8];
+        u[0] = sub_cc(a.l[0], MOD_L0);
+        u[1] = subc_cc(a.l[1], P::M1);
+        u[2] = subc_cc(a.l[2], P::M2);
+        u[3] = subc_cc(a.l[3], P::M3);
+        u[4] = subc_cc(a.l[4], 0);
+        u[5] = subc_cc(a.l[5], 0);
+        u[6] = subc_cc(a.l[6], 0);
+        u[7] = subc_cc(a.l[7], MOD_L7);
+        uint32_t borrow = subc(0, 0);  // 0xffffffff if a < m
+#pragma unroll
+        for (int i = 0; i < 8; i++) a.l[i] = borrow ? a.l[i] : u[i];
+    }
+
+    static ACC_HD fe_t add(const fe_t &a, const fe_t &b) {
+        fe_t r;
+        r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+        r.l[7] = addc(a.l[7], b.l[7]);  // both < 2^255: no carry out
+        reduce_once(r);
+        return r;
+    }
+    static ACC_HD fe_t dbl(const fe_t &a) { return add(a, a); }
+    static ACC_HD fe_t sub(const fe_t &a, const fe_t &b) {
+        fe_t r;
+        r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+        uint32_t mask = subc(0, 0);  // all ones if a < b
+        r.l[0] = add_cc(r.l[0], mask & MOD_L0);
+        r.l[1] = addc_cc(r.l[1], mask & P::M1);
+        r.l[2] = addc_cc(r.l[2], mask & P::M2);
+        r.l[3] = addc_cc(r.l[3], mask & P::M3);
+        r.l[4] = addc_cc(r.l[4], 0);
+        r.l[5] = addc_cc(r.l[5], 0);
+        r.l[6] = addc_cc(r.l[6], 0);
+        r.l[7] = addc(r.l[7], mask & MOD_L7);
+        return r;
+    }
+    static ACC_HD fe_t neg(const fe_t &a) { return sub(zero(), a); }
+
+    // Interleaved (CIOS) Montgomery product on two column-parity accumulators of 64-bit registers:
+    //   V = EV + OD * 2^32,   EV = sum ev[k] 2^(64k) (k < 5),   OD = sum od[k] 2^(64k) (k < 4).
+    // Products a[j]*b[i] with j even land 64-bit aligned in EV, j odd in OD, so every limb product is one
+    // IMAD.WIDE.U32.X in a carry chain.  After each round V is divided by 2^32, which swaps the roles of
+    // the two accumulators (pure renaming): EV' = OD + hi32(ev[0]), OD' = EV >> 64; the carry of that one
+    // 32-bit add is handed to the OD' chain, whose first limb has the same weight (2^32).
+    // Invariant: V < a + m after every round, so EV, OD < 2^256 and no chain overflows its top register.
+    // The result is canonicalised by one conditional subtraction.
+    static ACC_HD fe_t mul(const fe_t &A, const fe_t &B) {
+        const uint32_t *a = A.l, *b = B.l;
+        uint64_t ev[5], od[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) { ev[s] = mulw(a[2 * s], b[0]); od[s] = mulw(a[2 * s + 1], b[0]); }
+        ev[4] = 0;
+        const uint32_t k0 = opaque_zero();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i > 0) {
+                uint64_t nev[5], nod[4];
+                uint32_t t_lo = add_cc(lo32(od[0]), hi32(ev[0]));
+                nod[0] = addc_cc64(ev[1], mulw(a[1], b[i]));
+                nod[1] = addc_cc64(ev[2], mulw(a[3], b[i]));
+                nod[2] = addc_cc64(ev[3], mulw(a[5], b[i]));
+                nod[3] = addc64(ev[4], mulw(a[7], b[i]));
+                nev[0] = add_cc64(pack64(t_lo, hi32(od[0])), mulw(a[0], b[i]));
+                nev[1] = addc_cc64(od[1], mulw(a[2], b[i]));
+                nev[2] = addc_cc64(od[2], mulw(a[4], b[i]));
+                nev[3] = addc_cc64(od[3], mulw(a[6], b[i]));
+                nev[4] = addc64(0, 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { ev[k] = nev[k]; od[k] = nod[k]; }
+                ev[4] = nev[4];
+            }
+            // V += q * m, q = -V mod 2^32, m = [1, M1, M2, M3, 0, 0, 0, 2^30]
+            uint32_t q = 0u - lo32(ev[0]);
+            ev[0] = add_cc64(ev[0], (uint64_t)q);
+            ev[1] = addc_cc64(ev[1], mulw(q, P::M2));
+            ev[2] = addc_cc64(ev[2], ACC_MUL_WIDE_RIPPLES >= 2 ? mulw(q, k0) : 0ull);
+            ev[3] = addc_cc64(ev[3], ACC_MUL_WIDE_RIPPLES >= 3 ? mulw(q, k0) : 0ull);
+            ev[4] = addc64(ev[4], 0);
+            od[0] = add_cc64(od[0], mulw(q, P::M1));
+            od[1] = addc_cc64(od[1], mulw(q, P::M3));
+            od[2] = addc_cc64(od[2], ACC_MUL_WIDE_RIPPLES >= 1 ? mulw(q, k0) : 0ull);
+            od[3] = addc64(od[3], mulw(q, MOD_L7));
+        }
+        fe_t r;  // (EV + OD 2^32) / 2^32, lo32(ev[0]) == 0
+        r.l[0] = add_cc(hi32(ev[0]), lo32(od[0]));
+        r.l[1] = addc_cc(lo32(ev[1]), hi32(od[0]));
+        r.l[2] = addc_cc(hi32(ev[1]), lo32(od[1]));
+        r.l[3] = addc_cc(lo32(ev[2]), hi32(od[1]));
+        r.l[4] = addc_cc(hi32(ev[2]), lo32(od[2]));
+        r.l[5] = addc_cc(lo32(ev[3]), hi32(od[2]));
+        r.l[6] = addc_cc(hi32(ev[3]), lo32(od[3]));
+        r.l[7] = addc(lo32(ev[4]), hi32(od[3]));
+        reduce_once(r);
+        return r;
+    }
+    static ACC_HD fe_t sqr(const fe_t &a) { return mul(a, a); }
+
+    // into_repr(): Montgomery image -> canonical integer = a * 1 * R^-1
+    static ACC_HD fe_t from_mont(const fe_t &a) {
+        fe_t o = zero();
+        o.l[0] = 1u;
+        return mul(a, o);
+    }
+    static ACC_HD fe_t to_mont(const fe_t &a) { return mul(a, r2()); }
+
+    // a^(m-2) (Fermat); inv(0) = 0.  m - 2 has limbs [0xffffffff, M1-1, M2, M3, 0, 0, 0, 2^30].
+    static ACC_HD fe_t inv(const fe_t &a) {
+        fe_t acc = one();
+        const uint32_t e[8] = {0xffffffffu, P::M1 - 1u, P::M2, P::M3, 0u, 0u, 0u, MOD_L7};
+        for (int i = 254; i >= 0; i--) {
+            acc = sqr(acc);
+            if ((e[i >> 5] >> (i & 31)) & 1u) acc = mul(acc, a);
+        }
+        return acc;
+    }
+};
+
+}  // namespace accmsm
