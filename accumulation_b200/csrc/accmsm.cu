@@ -1,0 +1,543 @@
+// Host side of libaccmsm.so: context, HBM-resident commitment keys, kernel orchestration and the C-ABI
+// declared in include/accmsm.h.  No CPU arithmetic path exists here: every group / field operation is a
+// CUDA kernel from msm.cuh / vec.cuh, and every entry point fails with ACCMSM_E_CUDA without a device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/accmsm.h"
+#include "msm.cuh"
+#include "vec.cuh"
+
+using namespace accmsm;
+
+namespace {
+
+enum Stage { ST_H2D = 0, ST_DIGITS, ST_SCAN, ST_SCATTER, ST_ACCUMULATE, ST_REDUCE, ST_FINISH, ST_D2H, ST_COUNT };
+const char *STAGE_NAMES[ST_COUNT] = {"h2d", "digits", "scan", "scatter", "accumulate", "bucket_reduce", "finish", "d2h"};
+
+struct Bases {
+    int curve = 0;
+    size_t n = 0;
+    affine_t *d_xy = nullptr;
+    uint8_t *d_inf = nullptr;   // nullptr when no base is the identity
+};
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct accmsm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string last_error;
+    std::unordered_map<uint64_t, Bases> bases;
+    uint64_t next_handle = 1;
+    int window_bits = 0;
+    uint64_t launches = 0;
+    int acc_ctas_per_sm[2] = {0, 0};
+
+    // MSM workspace
+    DevBuf<uint32_t> digits, hist, offsets, cursor, entries, cta_ids;
+    DevBuf<xyzz_t> buckets, red_sum[2], red_wsum[2], cta_parts, partial;
+    DevBuf<uint8_t> scalars, misc;
+    affine_t *d_out_affine = nullptr;
+    uint32_t *d_out_inf = nullptr;
+    uint64_t *h_out = nullptr;   // pinned: 8 u64 affine + 1 u64 inf + 16 u64 partial
+    cudaEvent_t ev[ST_COUNT + 1];
+    bool ev_valid[ST_COUNT + 1];
+    float timings[ST_COUNT];
+};
+
+namespace {
+
+#define CU(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);            \
+            return _e == cudaErrorMemoryAllocation ? ACCMSM_E_NOMEM : ACCMSM_E_CUDA;           \
+        }                                                                                      \
+    } while (0)
+
+int fail_arg(accmsm_ctx *ctx, const char *msg) {
+    if (ctx) ctx->last_error = msg;
+    return ACCMSM_E_ARG;
+}
+
+void mark(accmsm_ctx *ctx, int idx, cudaStream_t st) {
+    cudaEventRecord(ctx->ev[idx], st);
+    ctx->ev_valid[idx] = true;
+}
+void clear_marks(accmsm_ctx *ctx) {
+    for (int i = 0; i <= ST_COUNT; i++) ctx->ev_valid[i] = false;
+    for (int i = 0; i < ST_COUNT; i++) ctx->timings[i] = 0.f;
+}
+// timings[i] = elapsed between mark i and the next valid mark
+void collect_timings(accmsm_ctx *ctx) {
+    int prev = -1;
+    for (int i = 0; i <= ST_COUNT; i++) {
+        if (!ctx->ev_valid[i]) continue;
+        if (prev >= 0) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev[prev], ctx->ev[i]) == cudaSuccess) ctx->timings[prev] = ms;
+        }
+        prev = i;
+    }
+}
+
+uint32_t pick_window_bits(const accmsm_ctx *ctx, size_t n) {
+    if (ctx->window_bits >= 2 && ctx->window_bits <= 16) return (uint32_t)ctx->window_bits;
+    uint32_t lg = 0;
+    while ((size_t(1) << (lg + 1)) <= n) lg++;
+    int c = (int)lg - 3;
+    return (uint32_t)std::min(16, std::max(4, c));
+}
+
+MsmShape make_shape(const accmsm_ctx *ctx, size_t n) {
+    MsmShape sh;
+    sh.n = (uint32_t)n;
+    sh.c = pick_window_bits(ctx, n);
+    sh.nwin = (256 + sh.c - 1) / sh.c;
+    sh.nb = 1u << (sh.c - 1);
+    sh.nkeys = sh.nwin * sh.nb;
+    return sh;
+}
+
+// The MSM pipeline after the digits kernel has been chosen.  Leaves the per-window sums combined into
+// either a device partial (d_partial) or the normalised affine result in ctx->d_out_affine/d_out_inf.
+template <int CURVE, class Src>
+int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src &src, const uint8_t *d_inf,
+            const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st) {
+    MsmShape sh = make_shape(ctx, n);
+    const size_t n_entries = (size_t)sh.n * sh.nwin;
+    CU(ctx, ctx->digits.ensure(n_entries));
+    CU(ctx, ctx->entries.ensure(n_entries));
+    CU(ctx, ctx->hist.ensure(sh.nkeys));
+    CU(ctx, ctx->offsets.ensure(sh.nkeys + 1));
+    CU(ctx, ctx->cursor.ensure(sh.nkeys));
+    CU(ctx, ctx->buckets.ensure(sh.nkeys));
+
+    mark(ctx, ST_DIGITS, st);
+    CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), st));
+    {
+        uint32_t blocks = (sh.n + 255) / 256;
+        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, d_inf, ctx->digits.p, ctx->hist.p);
+        ctx->launches++;
+    }
+    mark(ctx, ST_SCAN, st);
+    k_scan<<<1, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p);
+    ctx->launches++;
+    mark(ctx, ST_SCATTER, st);
+    {
+        uint32_t blocks = (sh.n + 255) / 256;
+        k_scatter<<<blocks, 256, 0, st>>>(sh, ctx->digits.p, ctx->cursor.p, ctx->entries.p);
+        ctx->launches++;
+    }
+    mark(ctx, ST_ACCUMULATE, st);
+    {
+        // grid: a whole number of resident waves, shrunk for small inputs so every thread still gets a
+        // few entries (upper bound n * nwin; the real count is only known on the device)
+        int per_sm = ctx->acc_ctas_per_sm[CURVE];
+        uint32_t gmax = (uint32_t)(ctx->sm_count * per_sm);
+        uint32_t want = (uint32_t)((n_entries + (size_t)ACC_THREADS * 8 - 1) / ((size_t)ACC_THREADS * 8));
+        uint32_t grid = std::max(1u, std::min(gmax, want));
+        CU(ctx, ctx->cta_ids.ensure(2 * grid));
+        CU(ctx, ctx->cta_parts.ensure(2 * grid));
+        size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
+        k_accumulate<CURVE><<<grid, ACC_THREADS, smem, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p,
+                                                              B.d_xy + offset, ctx->buckets.p,
+                                                              ctx->cta_ids.p, ctx->cta_parts.p);
+        uint32_t ns = 2 * grid;
+        size_t smem2 = ns * (sizeof(xyzz_t) + sizeof(uint32_t));
+        k_fixup<CURVE><<<1, FIX_THREADS, smem2, st>>>(ctx->cta_ids.p, ctx->cta_parts.p, ns, ctx->buckets.p);
+        ctx->launches += 2;
+    }
+    mark(ctx, ST_REDUCE, st);
+    const xyzz_t *window_sums = nullptr;
+    {
+        uint32_t seg = std::min<uint32_t>(RED0_SEG, sh.nb);
+        uint32_t per_set = sh.nb / seg;
+        uint32_t items = per_set * sh.nwin;
+        CU(ctx, ctx->red_sum[0].ensure(items));
+        CU(ctx, ctx->red_wsum[0].ensure(items));
+        CU(ctx, ctx->red_sum[1].ensure(items / 32 + sh.nwin));
+        CU(ctx, ctx->red_wsum[1].ensure(items / 32 + sh.nwin));
+        k_reduce0<CURVE><<<(items + 127) / 128, 128, 0, st>>>(ctx->offsets.p, ctx->buckets.p, sh.nb, seg, items,
+                                                              ctx->red_sum[0].p, ctx->red_wsum[0].p);
+        ctx->launches++;
+        uint32_t log2_span = 0;
+        while ((1u << log2_span) < seg) log2_span++;
+        int cur = 0;
+        while (per_set > 1) {
+            uint32_t per_out = (per_set + 31) / 32;
+            uint32_t warps = per_out * sh.nwin;
+            k_reduce1<CURVE><<<(warps * 32 + 127) / 128, 128, 0, st>>>(ctx->red_sum[cur].p, ctx->red_wsum[cur].p, per_set,
+                                                                       per_out, sh.nwin, log2_span,
+                                                                       ctx->red_sum[cur ^ 1].p, ctx->red_wsum[cur ^ 1].p);
+            ctx->launches++;
+            log2_span += 5;
+            per_set = per_out;
+            cur ^= 1;
+        }
+        window_sums = ctx->red_wsum[cur].p;
+    }
+    mark(ctx, ST_FINISH, st);
+    k_finish<CURVE><<<1, 32, 0, st>>>(window_sums, sh.nwin, sh.c, d_extra, n_extra, normalise ? 1 : 0, d_partial,
+                                      ctx->d_out_affine, ctx->d_out_inf);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    return ACCMSM_OK;
+}
+
+// normalised result -> host
+int fetch_affine(accmsm_ctx *ctx, uint64_t out_xy[8], uint8_t *out_inf, cudaStream_t st) {
+    mark(ctx, ST_D2H, st);
+    CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, 64, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(ctx->h_out + 8, ctx->d_out_inf, 4, cudaMemcpyDeviceToHost, st));
+    mark(ctx, ST_COUNT, st);
+    CU(ctx, cudaStreamSynchronize(st));
+    memcpy(out_xy, ctx->h_out, 64);
+    *out_inf = (uint8_t)(*(uint32_t *)(ctx->h_out + 8) != 0);
+    collect_timings(ctx);
+    return ACCMSM_OK;
+}
+
+int write_identity(accmsm_ctx *ctx, int curve, uint64_t out_xy[8], uint8_t *out_inf) {
+    (void)ctx;
+    static const uint64_t R_P[4] = {0x34786d38fffffffdULL, 0x992c350be41914adULL, 0xffffffffffffffffULL, 0x3fffffffffffffffULL};
+    static const uint64_t R_Q[4] = {0x5b2b3e9cfffffffdULL, 0x992c350be3420567ULL, 0xffffffffffffffffULL, 0x3fffffffffffffffULL};
+    memset(out_xy, 0, 32);
+    memcpy(out_xy + 4, curve == 0 ? R_P : R_Q, 32);
+    *out_inf = 1;
+    return ACCMSM_OK;
+}
+
+const Bases *find_bases(accmsm_ctx *ctx, uint64_t handle) {
+    auto it = ctx->bases.find(handle);
+    if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return nullptr; }
+    return &it->second;
+}
+
+// MSM of host scalars, one vector.  d_extra/n_extra: XYZZ partials added before normalisation.
+int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint64_t *scalars, int mont,
+                     const xyzz_t *d_extra, uint32_t n_extra, uint64_t out_xy[8], uint8_t *out_inf) {
+    cudaStream_t st = ctx->stream;
+    clear_marks(ctx);
+    CU(ctx, ctx->scalars.ensure(n * 32));
+    mark(ctx, ST_H2D, st);
+    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    const uint8_t *d_inf = B.d_inf ? B.d_inf + offset : nullptr;
+    int rc;
+    if (B.curve == 0) {
+        MemScalars<1> src{ctx->scalars.p, mont};
+        rc = run_msm<0>(ctx, B, offset, n, src, d_inf, d_extra, n_extra, nullptr, true, st);
+    } else {
+        MemScalars<0> src{ctx->scalars.p, mont};
+        rc = run_msm<1>(ctx, B, offset, n, src, d_inf, d_extra, n_extra, nullptr, true, st);
+    }
+    if (rc) return rc;
+    return fetch_affine(ctx, out_xy, out_inf, st);
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C-ABI
+// =====================================================================================================
+extern "C" {
+
+const char *accmsm_strerror(int code) {
+    switch (code) {
+        case ACCMSM_OK: return "ok";
+        case ACCMSM_E_CUDA: return "CUDA runtime error";
+        case ACCMSM_E_ARG: return "invalid argument";
+        case ACCMSM_E_HANDLE: return "unknown bases handle";
+        case ACCMSM_E_NOMEM: return "out of device or pinned memory";
+        default: return "unknown error";
+    }
+}
+
+const char *accmsm_last_error(accmsm_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null ctx"; }
+
+const char *accmsm_stage_name(int stage) { return stage >= 0 && stage < ST_COUNT ? STAGE_NAMES[stage] : ""; }
+
+int accmsm_init(accmsm_ctx **out, int device) {
+    if (!out) return ACCMSM_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return ACCMSM_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ACCMSM_E_CUDA;
+    accmsm_ctx *ctx = new accmsm_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
+    for (int i = 0; i <= ST_COUNT; i++) { cudaEventCreate(&ctx->ev[i]); ctx->ev_valid[i] = false; }
+    bool ok = cudaMalloc(&ctx->d_out_affine, sizeof(affine_t)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_out_inf, 16) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_out, 32 * sizeof(uint64_t)) == cudaSuccess;
+    // shared-memory opt-in and resident CTAs per SM for the accumulate kernels
+    size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
+    size_t smem_fix = (size_t)FIX_THREADS * FIX_PER_T * (sizeof(xyzz_t) + sizeof(uint32_t));
+    ok = ok && cudaFuncSetAttribute(k_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_accumulate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_fixup<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem_fix, 227 * 1024)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_fixup<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem_fix, 227 * 1024)) == cudaSuccess;
+    if (ok) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->acc_ctas_per_sm[0], k_accumulate<0>, ACC_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->acc_ctas_per_sm[1], k_accumulate<1>, ACC_THREADS, smem);
+        for (int c = 0; c < 2; c++) {
+            if (ctx->acc_ctas_per_sm[c] < 1) ctx->acc_ctas_per_sm[c] = 1;
+            // k_fixup holds 2 slots per accumulate CTA: at most FIX_THREADS * FIX_PER_T slots
+            int cap = (FIX_THREADS * FIX_PER_T / 2) / ctx->sm_count;
+            if (ctx->acc_ctas_per_sm[c] > cap) ctx->acc_ctas_per_sm[c] = std::max(1, cap);
+        }
+    }
+    if (!ok) {
+        ctx->last_error = cudaGetErrorString(cudaGetLastError());
+        accmsm_destroy(ctx);
+        return ACCMSM_E_CUDA;
+    }
+    *out = ctx;
+    return ACCMSM_OK;
+}
+
+void accmsm_destroy(accmsm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->bases) { cudaFree(kv.second.d_xy); if (kv.second.d_inf) cudaFree(kv.second.d_inf); }
+    ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
+    ctx->cta_ids.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
+    ctx->scalars.release(); ctx->misc.release();
+    for (int i = 0; i < 2; i++) { ctx->red_sum[i].release(); ctx->red_wsum[i].release(); }
+    if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
+    if (ctx->d_out_inf) cudaFree(ctx->d_out_inf);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int accmsm_set_window_bits(accmsm_ctx *ctx, int c) {
+    if (!ctx || c < 0 || c > 16 || c == 1) return fail_arg(ctx, "window bits must be 0 (auto) or 2..16");
+    ctx->window_bits = c;
+    return ACCMSM_OK;
+}
+
+uint64_t accmsm_kernel_launches(accmsm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int accmsm_last_timings(accmsm_ctx *ctx, float *ms_out, int max_stages) {
+    if (!ctx || !ms_out) return ACCMSM_E_ARG;
+    int k = std::min<int>(max_stages, ST_COUNT);
+    for (int i = 0; i < k; i++) ms_out[i] = ctx->timings[i];
+    return k;
+}
+
+int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const uint8_t *infinity, size_t n,
+                          uint64_t *handle) {
+    if (!ctx || !handle || (curve != 0 && curve != 1) || (n && !xy)) return fail_arg(ctx, "register_bases: bad argument");
+    if (n >= (size_t(1) << 31)) return fail_arg(ctx, "register_bases: n must be < 2^31");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Bases B;
+    B.curve = curve; B.n = n;
+    CU(ctx, cudaMalloc(&B.d_xy, std::max<size_t>(n, 1) * sizeof(affine_t)));
+    if (n) CU(ctx, cudaMemcpyAsync(B.d_xy, xy, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+    bool any_inf = false;
+    if (infinity) for (size_t i = 0; i < n && !any_inf; i++) any_inf = infinity[i] != 0;
+    if (any_inf) {
+        CU(ctx, cudaMalloc(&B.d_inf, n));
+        CU(ctx, cudaMemcpyAsync(B.d_inf, infinity, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *handle = ctx->next_handle++;
+    ctx->bases[*handle] = B;
+    return ACCMSM_OK;
+}
+
+int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle) {
+    if (!ctx) return ACCMSM_E_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->bases.find(handle);
+    if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(it->second.d_xy);
+    if (it->second.d_inf) cudaFree(it->second.d_inf);
+    ctx->bases.erase(it);
+    return ACCMSM_OK;
+}
+
+int accmsm_msm(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const uint64_t *scalars,
+               int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf) {
+    if (!ctx || !out_xy || !out_inf || (n && !scalars)) return fail_arg(ctx, "msm: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "msm: range exceeds registered bases");
+    if (n == 0) return write_identity(ctx, B->curve, out_xy, out_inf);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return msm_host_scalars(ctx, *B, offset, n, scalars, scalars_montgomery, nullptr, 0, out_xy, out_inf);
+}
+
+int accmsm_msm_batch(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars,
+                     int scalars_montgomery, uint64_t *out_xy, uint8_t *out_inf) {
+    if (!ctx || !out_xy || !out_inf || (n && k && !scalars)) return fail_arg(ctx, "msm_batch: bad argument");
+    for (size_t j = 0; j < k; j++) {
+        int rc = accmsm_msm(ctx, handle, offset, n, scalars + j * n * 4, scalars_montgomery, out_xy + 8 * j, out_inf + j);
+        if (rc) return rc;
+    }
+    return ACCMSM_OK;
+}
+
+int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *elems_mont, size_t hiding_index,
+                  const uint64_t *randomizer_mont, uint64_t out_xy[8], uint8_t *out_inf) {
+    if (!ctx || !out_xy || !out_inf || (n && !elems_mont)) return fail_arg(ctx, "commit: bad argument");
+    if (!randomizer_mont) return accmsm_msm(ctx, handle, 0, n, elems_mont, 1, out_xy, out_inf);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (n > B->n || hiding_index >= B->n) return fail_arg(ctx, "commit: range exceeds registered bases");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // randomizer * hiding_generator as a one-point MSM whose XYZZ partial is folded into the main MSM's finish
+    CU(ctx, ctx->partial.ensure(1));
+    CU(ctx, ctx->scalars.ensure(std::max<size_t>(n, 1) * 32));
+    clear_marks(ctx);
+    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, randomizer_mont, 32, cudaMemcpyHostToDevice, st));
+    int rc;
+    const uint8_t *d_inf1 = B->d_inf ? B->d_inf + hiding_index : nullptr;
+    if (B->curve == 0) { MemScalars<1> s1{ctx->scalars.p, 1}; rc = run_msm<0>(ctx, *B, hiding_index, 1, s1, d_inf1, nullptr, 0, ctx->partial.p, false, st); }
+    else { MemScalars<0> s1{ctx->scalars.p, 1}; rc = run_msm<1>(ctx, *B, hiding_index, 1, s1, d_inf1, nullptr, 0, ctx->partial.p, false, st); }
+    if (rc) return rc;
+    if (n == 0) {
+        if (B->curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, ctx->partial.p, 1, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
+        else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, ctx->partial.p, 1, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
+        ctx->launches++;
+        return fetch_affine(ctx, out_xy, out_inf, st);
+    }
+    return msm_host_scalars(ctx, *B, 0, n, elems_mont, 1, ctx->partial.p, 1, out_xy, out_inf);
+}
+
+int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
+                           int scalars_montgomery, void *d_out_partial, void *stream) {
+    if (!ctx || !d_out_partial || (n && !d_scalars)) return fail_arg(ctx, "msm_partial_dev: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "msm_partial_dev: range exceeds registered bases");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    clear_marks(ctx);
+    int rc;
+    if (n == 0) {
+        if (B->curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, (xyzz_t *)d_out_partial, nullptr, nullptr);
+        else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, (xyzz_t *)d_out_partial, nullptr, nullptr);
+        ctx->launches++;
+        rc = ACCMSM_OK;
+    } else {
+        const uint8_t *d_inf = B->d_inf ? B->d_inf + offset : nullptr;
+        if (B->curve == 0) { MemScalars<1> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<0>(ctx, *B, offset, n, src, d_inf, nullptr, 0, (xyzz_t *)d_out_partial, false, st); }
+        else { MemScalars<0> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<1>(ctx, *B, offset, n, src, d_inf, nullptr, 0, (xyzz_t *)d_out_partial, false, st); }
+    }
+    if (rc) return rc;
+    mark(ctx, ST_COUNT, st);
+    if (!stream) { CU(ctx, cudaStreamSynchronize(st)); collect_timings(ctx); }
+    return ACCMSM_OK;
+}
+
+int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k, uint64_t out_xy[8],
+                                uint8_t *out_inf) {
+    if (!ctx || !out_xy || !out_inf || (k && !d_partials) || (curve != 0 && curve != 1)) return fail_arg(ctx, "combine_partials: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    clear_marks(ctx);
+    mark(ctx, ST_FINISH, st);
+    if (curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
+    else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
+    ctx->launches++;
+    return fetch_affine(ctx, out_xy, out_inf, st);
+}
+
+static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_mont, int k, size_t coeff_offset, size_t n,
+                   xyzz_t *d_partial, bool normalise, cudaStream_t st) {
+    CU(ctx, ctx->misc.ensure(64 * 32));
+    CU(ctx, cudaMemcpyAsync(ctx->misc.p, challenges_mont, (size_t)k * 32, cudaMemcpyHostToDevice, st));
+    if (B.curve == 0) { IpaScalars<1> src{ctx->misc.p, k, (uint32_t)coeff_offset}; return run_msm<0>(ctx, B, 0, n, src, B.d_inf, nullptr, 0, d_partial, normalise, st); }
+    IpaScalars<0> src{ctx->misc.p, k, (uint32_t)coeff_offset};
+    return run_msm<1>(ctx, B, 0, n, src, B.d_inf, nullptr, 0, d_partial, normalise, st);
+}
+
+int accmsm_ipa_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k, uint64_t out_xy[8],
+                         uint8_t *out_inf) {
+    if (!ctx || !out_xy || !out_inf || !challenges_mont || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    size_t n = size_t(1) << k;
+    if (n > B->n) return fail_arg(ctx, "ipa_final_key: key shorter than 2^k");
+    CU(ctx, cudaSetDevice(ctx->device));
+    clear_marks(ctx);
+    mark(ctx, ST_H2D, ctx->stream);
+    int rc = ipa_run(ctx, *B, challenges_mont, k, 0, n, nullptr, true, ctx->stream);
+    if (rc) return rc;
+    return fetch_affine(ctx, out_xy, out_inf, ctx->stream);
+}
+
+int accmsm_ipa_check_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k,
+                               const uint64_t expected_xy[8], uint8_t expected_inf, int *accept, uint64_t out_xy[8],
+                               uint8_t *out_inf) {
+    if (!accept || !expected_xy) return fail_arg(ctx, "ipa_check_final_key: bad argument");
+    uint64_t xy[8]; uint8_t inf = 0;
+    int rc = accmsm_ipa_final_key(ctx, handle, challenges_mont, k, xy, &inf);
+    if (rc) return rc;
+    // affine equality exactly as GroupAffine's PartialEq: both identity, or same (x, y)
+    *accept = (inf || expected_inf) ? (inf != 0) == (expected_inf != 0) : memcmp(xy, expected_xy, 64) == 0;
+    if (out_xy) memcpy(out_xy, xy, 64);
+    if (out_inf) *out_inf = inf;
+    return ACCMSM_OK;
+}
+
+int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k,
+                                     size_t coeff_offset, size_t n, void *d_out_partial, void *stream) {
+    if (!ctx || !d_out_partial || !challenges_mont || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key_partial_dev: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (n == 0 || n > B->n || coeff_offset + n > (size_t(1) << k)) return fail_arg(ctx, "ipa_final_key_partial_dev: bad range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    clear_marks(ctx);
+    int rc = ipa_run(ctx, *B, challenges_mont, k, coeff_offset, n, (xyzz_t *)d_out_partial, false, st);
+    if (rc) return rc;
+    mark(ctx, ST_COUNT, st);
+    if (!stream) { CU(ctx, cudaStreamSynchronize(st)); collect_timings(ctx); }
+    return ACCMSM_OK;
+}
+
+}  // extern "C"
+
+#include "vec_api.inc"

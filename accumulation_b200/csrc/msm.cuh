@@ -1,0 +1,444 @@
+// Pippenger variable-base MSM for sm_100a (K2 of SURVEY.md 2b).  Replaces
+// ark_ec::msm::VariableBaseMSM::multi_scalar_mul (ark-ec 0.2.0) as reached from
+// PedersenCommitment::commit / IpaPC::cm_commit (reference call sites: src/hp_as/mod.rs:196,197,214,377,
+// 910-918; src/r1cs_nark_as/r1cs_nark/mod.rs:216-261,375-407; src/ipa_pc_as/mod.rs:155,454-462,836-845).
+//
+// Pipeline (all on one stream, no host round trips):
+//   k_digits      scalar -> (optional from-Montgomery) -> signed radix-2^c digits, histogram of bucket keys
+//   k_scan        exclusive prefix sum of the histogram -> bucket offsets + scatter cursors
+//   k_scatter     counting-sort scatter of (point index | sign) into bucket order
+//   k_accumulate  perfectly balanced segmented accumulation: every thread sums an equal-length slice of
+//                 the sorted entry list with XYZZ mixed additions; runs that straddle thread / CTA
+//                 boundaries are merged by a segmented scan in shared memory (hot buckets are
+//                 tree-reduced, never serialised: constant scalar vectors cost the same as random ones)
+//   k_fixup       merges the two boundary partials of every CTA
+//   k_reduce0/1   bucket reduction sum_b b*B_b: thread-serial running sums over 16 buckets, then
+//                 warp-parallel suffix scans over 32 items per level
+//   k_finish      Horner combine of the window sums (c doublings per window), optional normalisation
+#pragma once
+#include <cuda_runtime.h>
+#include "ec.cuh"
+
+namespace accmsm {
+
+constexpr uint32_t NONE_ID = 0xffffffffu;
+constexpr int ACC_THREADS = 256;       // threads per accumulate CTA
+constexpr int FIX_THREADS = 512;       // k_fixup: one CTA, FIX_PER_T slots per thread (<= 1536 slots fit in 227 KB)
+constexpr int FIX_PER_T = 3;
+constexpr int RED0_SEG = 16;           // buckets per thread in the first reduction level
+constexpr int MAX_WINDOWS = 64;
+
+struct MsmShape {
+    uint32_t n;        // number of (base, scalar) pairs
+    uint32_t c;        // window bits
+    uint32_t nwin;     // number of signed windows = ceil(256 / c)
+    uint32_t nb;       // buckets per window = 2^(c-1)
+    uint32_t nkeys;    // nwin * nb
+};
+
+// ------------------------------------------------------------------------------------------------
+// vectorised loads / stores (128-bit, coalesced when consecutive threads touch consecutive records)
+// ------------------------------------------------------------------------------------------------
+ACC_D fe_t load_fe(const void *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    fe_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+ACC_D fe_t load_fe_nc(const void *p) {   // read-only path for data that is streamed once
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fe_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+ACC_D void store_fe(void *p, const fe_t &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
+    q[1] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
+}
+ACC_D affine_t load_affine(const affine_t *p) {
+    affine_t r;
+    r.x = load_fe_nc(&p->x); r.y = load_fe_nc(&p->y);
+    return r;
+}
+ACC_D xyzz_t load_xyzz(const xyzz_t *p) {
+    xyzz_t r;
+    r.x = load_fe(&p->x); r.y = load_fe(&p->y); r.zz = load_fe(&p->zz); r.zzz = load_fe(&p->zzz);
+    return r;
+}
+ACC_D void store_xyzz(xyzz_t *p, const xyzz_t &r) {
+    store_fe(&p->x, r.x); store_fe(&p->y, r.y); store_fe(&p->zz, r.zz); store_fe(&p->zzz, r.zzz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar sources for k_digits
+// ------------------------------------------------------------------------------------------------
+// Scalars resident in HBM: n x 32 B, either the Fp256 Montgomery image (what PedersenCommitment::commit
+// receives; into_repr() is done here) or canonical BigInteger256 (what VariableBaseMSM receives).
+template <int SFIELD> struct MemScalars {
+    const uint8_t *ptr;
+    int montgomery;
+    ACC_D fe_t canonical(uint32_t i) const {
+        fe_t s = load_fe_nc(ptr + (size_t)i * 32);
+        if (montgomery) s = Fp<SFIELD>::from_mont(s);
+        return s;
+    }
+};
+// K3: coefficients of the IPA succinct-check polynomial h(X) = prod_{i=1..k} (1 + xi_i X^(2^(k-i)))
+// generated on the fly (never materialised in HBM): coeff[j] = prod_{i : bit (k-i) of j set} xi_i
+// (ark-poly-commit SuccinctCheckPolynomial::compute_coeffs; reference call sites
+// src/ipa_pc_as/mod.rs:400 and :836 via IpaPC::check).  `offset` lets a GPU own a slice of the key.
+template <int SFIELD> struct IpaScalars {
+    const uint8_t *challenges;  // k x 32 B Montgomery, xi_1 first
+    int k;
+    uint32_t offset;
+    ACC_D fe_t coeff_mont(uint32_t i) const {
+        uint32_t j = i + offset;
+        fe_t acc = Fp<SFIELD>::one();
+        for (int b = 0; b < k; b++) {          // bit b of j <-> challenge index k - b  (1-based)
+            if ((j >> b) & 1u) acc = Fp<SFIELD>::mul(acc, load_fe(challenges + (size_t)(k - 1 - b) * 32));
+        }
+        return acc;
+    }
+    ACC_D fe_t canonical(uint32_t i) const { return Fp<SFIELD>::from_mont(coeff_mont(i)); }
+};
+
+// bits [pos, pos + c) of a 256-bit little-endian integer, c <= 24
+ACC_D uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
+    uint32_t limb = pos >> 5, off = pos & 31;
+    uint32_t lo = limb < 8 ? s[limb] : 0u;
+    uint32_t hi = limb + 1 < 8 ? s[limb + 1] : 0u;
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)(v >> off) & ((1u << c) - 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_digits: one thread per scalar.  digits[w * n + i] = 0 for a zero digit, else |d| | (d < 0) << 31.
+// ------------------------------------------------------------------------------------------------
+template <class Src>
+__global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint8_t *__restrict__ base_is_identity,
+                                                 uint32_t *__restrict__ digits, uint32_t *__restrict__ hist) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sh.n) return;
+    fe_t s = src.canonical(i);
+    if (base_is_identity && base_is_identity[i]) s = Fp<0>::zero();   // identity bases contribute nothing
+    const uint32_t half = 1u << (sh.c - 1);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < sh.nwin; w++) {
+        uint32_t raw = extract_bits(s.l, w * sh.c, sh.c) + carry;
+        uint32_t enc = 0;
+        if (raw > half) {             // negative digit raw - 2^c, borrow one from the next window
+            uint32_t mag = (1u << sh.c) - raw;
+            carry = 1;
+            enc = mag ? (mag | 0x80000000u) : 0u;   // raw == 2^c -> digit 0 with carry
+        } else {
+            carry = 0;
+            enc = raw;
+        }
+        digits[(size_t)w * sh.n + i] = enc;
+        uint32_t mag = enc & 0x7fffffffu;
+        if (mag) atomicAdd(&hist[w * sh.nb + mag - 1], 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scan: exclusive scan of hist[0..nkeys) into offsets[0..nkeys] and cursor[0..nkeys); one CTA.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict__ hist, uint32_t nkeys,
+                                                uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    // tiles of 1024 * 4 keys; each thread owns 4 consecutive keys of the tile (one 128-bit load)
+    for (uint32_t base = 0; base < nkeys; base += 4096) {
+        uint32_t k0 = base + tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (k0 + j < nkeys) ? hist[k0 + j] : 0u;
+        uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane];
+            uint32_t wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sums[lane] = wi - ws;  // exclusive prefix of warp sums
+        }
+        __syncthreads();
+        uint32_t excl = carry_s + warp_sums[wid] + incl - tsum;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (k0 + j < nkeys) { offsets[k0 + j] = excl; cursor[k0 + j] = excl; }
+            excl += v[j];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = excl;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[nkeys] = carry_s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scatter: entries[cursor[key]++] = point index | sign
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__restrict__ digits,
+                                                  uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sh.n) return;
+    for (uint32_t w = 0; w < sh.nwin; w++) {
+        uint32_t enc = digits[(size_t)w * sh.n + i];
+        uint32_t mag = enc & 0x7fffffffu;
+        if (mag) {
+            uint32_t pos = atomicAdd(&cursor[w * sh.nb + mag - 1], 1u);
+            entries[pos] = i | (enc & 0x80000000u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// segmented inclusive scan of (id, point) slots in shared memory; slots with equal ids are contiguous.
+// After it, the last slot of every id-group holds the group's sum.  NS <= 2 * blockDim.x * SLOTS_PER_T.
+// ------------------------------------------------------------------------------------------------
+template <int CURVE, int PER_T>
+ACC_D void seg_scan(xyzz_t *pt, const uint32_t *id, uint32_t ns) {
+    using Cv = Curve<CURVE>;
+    // Hillis-Steele in place.  A step reads slot i - d and writes slot i; the slots are swept in PER_T
+    // phases from the top stripe down, so a phase only ever reads slots that this step has not written
+    // yet (writes of a phase land in its own stripe, reads come from it or from lower stripes) and one
+    // point per thread is live at a time.
+    for (uint32_t d = 1; d < ns; d <<= 1) {
+#pragma unroll 1
+        for (int r = PER_T - 1; r >= 0; r--) {
+            uint32_t i = threadIdx.x + r * blockDim.x;
+            bool doit = i < ns && i >= d && id[i] != NONE_ID && id[i] == id[i - d];
+            xyzz_t mine;
+            if (doit) { mine = pt[i]; xyzz_t other = pt[i - d]; Cv::add(mine, other); }
+            __syncthreads();
+            if (doit) pt[i] = mine;
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_accumulate
+// ------------------------------------------------------------------------------------------------
+template <int CURVE>
+__global__ void __launch_bounds__(ACC_THREADS, 2)
+k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_t *__restrict__ entries,
+             const affine_t *__restrict__ bases, xyzz_t *__restrict__ buckets,
+             uint32_t *__restrict__ cta_ids, xyzz_t *__restrict__ cta_parts) {
+    using Cv = Curve<CURVE>;
+    extern __shared__ uint4 smem_raw[];
+    xyzz_t *slot_pt = reinterpret_cast<xyzz_t *>(smem_raw);
+    uint32_t *slot_id = reinterpret_cast<uint32_t *>(slot_pt + 2 * ACC_THREADS);
+
+    const uint32_t M = offsets[nkeys];
+    const uint32_t T = gridDim.x * blockDim.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = (M + T - 1) / T;
+    const uint64_t s64 = (uint64_t)t * L;
+    const uint32_t s = s64 < M ? (uint32_t)s64 : M;
+    const uint32_t e = (s64 + L < M) ? (uint32_t)(s64 + L) : M;
+
+    xyzz_t head = Cv::identity(), tail = Cv::identity();
+    uint32_t head_id = NONE_ID, tail_id = NONE_ID;
+
+    if (s < e) {
+        // bucket containing entry s: first k with offsets[k + 1] > s
+        uint32_t lo = 0, hi = nkeys - 1;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (offsets[mid + 1] > s) hi = mid; else lo = mid + 1;
+        }
+        uint32_t k = lo, pos = s, nruns = 0;
+        while (pos < e) {
+            const uint32_t bend = offsets[k + 1];
+            const uint32_t rend = bend < e ? bend : e;
+            xyzz_t acc = Cv::identity();
+            for (uint32_t p = pos; p < rend; p++) {
+                uint32_t ent = entries[p];
+                affine_t pt = load_affine(bases + (ent & 0x7fffffffu));
+                if (ent >> 31) pt.y = Cv::F::neg(pt.y);
+                Cv::madd(acc, pt);
+            }
+            pos = rend;
+            if (nruns == 0) { head = acc; head_id = k; }
+            else if (pos < e) store_xyzz(buckets + k, acc);     // a run strictly inside this slice is complete
+            else { tail = acc; tail_id = k; }
+            nruns++;
+            if (pos < e) { do { k++; } while (offsets[k + 1] == pos); }
+        }
+        if (tail_id == NONE_ID) tail_id = head_id;   // keep equal ids contiguous for the segmented scan
+    }
+
+    slot_pt[2 * threadIdx.x] = head; slot_id[2 * threadIdx.x] = head_id;
+    slot_pt[2 * threadIdx.x + 1] = tail; slot_id[2 * threadIdx.x + 1] = tail_id;
+    __syncthreads();
+    const uint32_t ns = 2 * ACC_THREADS;
+    seg_scan<CURVE, 2>(slot_pt, slot_id, ns);
+
+    // ids of the first slot and of the last slot that holds work
+    const uint32_t first_id = slot_id[0];
+    __shared__ uint32_t last_id_s;
+    if (threadIdx.x == 0) last_id_s = NONE_ID;
+    __syncthreads();
+    for (int r = 0; r < 2; r++) {
+        uint32_t i = threadIdx.x + r * blockDim.x;
+        bool valid = slot_id[i] != NONE_ID;
+        bool next_valid = (i + 1 < ns) && slot_id[i + 1] != NONE_ID;
+        if (valid && !next_valid) last_id_s = slot_id[i];
+    }
+    __syncthreads();
+    const uint32_t last_id = last_id_s;
+    if (threadIdx.x == 0) {
+        cta_ids[2 * blockIdx.x] = first_id;
+        cta_ids[2 * blockIdx.x + 1] = last_id;
+        if (first_id == last_id) store_xyzz(cta_parts + 2 * blockIdx.x + 1, Cv::identity());
+    }
+    for (int r = 0; r < 2; r++) {
+        uint32_t i = threadIdx.x + r * blockDim.x;
+        uint32_t id = slot_id[i];
+        if (id == NONE_ID) continue;
+        bool group_end = (i + 1 == ns) || slot_id[i + 1] != id;
+        if (!group_end) continue;
+        if (id == first_id) store_xyzz(cta_parts + 2 * blockIdx.x, slot_pt[i]);
+        else if (id == last_id) store_xyzz(cta_parts + 2 * blockIdx.x + 1, slot_pt[i]);
+        else store_xyzz(buckets + id, slot_pt[i]);
+    }
+}
+
+// k_fixup: one CTA merges the 2 * G boundary partials left by k_accumulate and writes the buckets.
+template <int CURVE>
+__global__ void __launch_bounds__(FIX_THREADS) k_fixup(const uint32_t *__restrict__ cta_ids,
+                                                 const xyzz_t *__restrict__ cta_parts, uint32_t ns,
+                                                 xyzz_t *__restrict__ buckets) {
+    extern __shared__ uint4 smem_raw[];
+    xyzz_t *slot_pt = reinterpret_cast<xyzz_t *>(smem_raw);
+    uint32_t *slot_id = reinterpret_cast<uint32_t *>(slot_pt + ns);
+    for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
+        slot_id[i] = cta_ids[i];
+        slot_pt[i] = load_xyzz(cta_parts + i);
+    }
+    __syncthreads();
+    seg_scan<CURVE, FIX_PER_T>(slot_pt, slot_id, ns);
+    for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
+        uint32_t id = slot_id[i];
+        if (id == NONE_ID) continue;
+        bool group_end = (i + 1 == ns) || slot_id[i + 1] != id;
+        if (group_end) store_xyzz(buckets + id, slot_pt[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucket reduction  S_w = sum_{b=1..nb} b * B_{w,b}
+// ------------------------------------------------------------------------------------------------
+// level 0: one thread per RED0_SEG consecutive buckets: sum = sum_j B_j, wsum = sum_j (j + 1) B_j.
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_reduce0(const uint32_t *__restrict__ offsets, const xyzz_t *__restrict__ buckets,
+                                                  uint32_t nb, uint32_t seg, uint32_t nitems_total,
+                                                  xyzz_t *__restrict__ sum_out, xyzz_t *__restrict__ wsum_out) {
+    using Cv = Curve<CURVE>;
+    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= nitems_total) return;
+    const uint32_t per_set = nb / seg;
+    const uint32_t set = it / per_set, base = (it % per_set) * seg;
+    xyzz_t run = Cv::identity(), acc = Cv::identity();
+    for (int j = (int)seg - 1; j >= 0; j--) {
+        uint32_t k = set * nb + base + j;
+        if (offsets[k + 1] != offsets[k]) { xyzz_t b = load_xyzz(buckets + k); Cv::add(run, b); }
+        Cv::add(acc, run);
+    }
+    store_xyzz(sum_out + it, run);
+    store_xyzz(wsum_out + it, acc);
+}
+
+ACC_D xyzz_t shfl_down_xyzz(const xyzz_t &p, int d) {
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, p.x.l[i], d);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, p.y.l[i], d);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, p.zz.l[i], d);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, p.zzz.l[i], d);
+    }
+    return r;
+}
+
+// level >= 1: one warp per group of 32 consecutive items of a set, each item spanning `span` buckets:
+//   Sum = sum_j sum_j,  Wsum = sum_j wsum_j + span * sum_j j * sum_j
+// sum_j j*sum_j = sum_{j>=1} (suffix sum from j), by a Kogge-Stone suffix scan + warp reduction.
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_reduce1(const xyzz_t *__restrict__ sum_in, const xyzz_t *__restrict__ wsum_in,
+                                                  uint32_t per_set_in, uint32_t per_set_out, uint32_t nsets,
+                                                  uint32_t log2_span, xyzz_t *__restrict__ sum_out,
+                                                  xyzz_t *__restrict__ wsum_out) {
+    using Cv = Curve<CURVE>;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nsets * per_set_out) return;   // whole warp exits together
+    const uint32_t set = warp / per_set_out, grp = warp % per_set_out;
+    const uint32_t j = grp * 32 + lane;
+    const bool valid = j < per_set_in;
+    xyzz_t run = Cv::identity(), ws = Cv::identity();
+    if (valid) { run = load_xyzz(sum_in + set * per_set_in + j); ws = load_xyzz(wsum_in + set * per_set_in + j); }
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {   // suffix scan: run_j = sum_{i >= j} sum_i
+        xyzz_t o = shfl_down_xyzz(run, d);
+        if (lane + d < 32) Cv::add(run, o);
+    }
+    xyzz_t tot = run;                     // lane 0 holds Sum
+    xyzz_t jr = lane >= 1 ? run : Cv::identity();
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {   // reductions: sum_{j>=1} run_j  and  sum_j wsum_j
+        xyzz_t o = shfl_down_xyzz(jr, d);
+        xyzz_t o2 = shfl_down_xyzz(ws, d);
+        if (lane < d) { Cv::add(jr, o); Cv::add(ws, o2); }
+    }
+    if (lane == 0) {
+        for (uint32_t b = 0; b < log2_span; b++) jr = Cv::dbl(jr);
+        Cv::add(ws, jr);
+        store_xyzz(sum_out + warp, tot);
+        store_xyzz(wsum_out + warp, ws);
+    }
+}
+
+// k_finish: out = sum_w 2^(c w) S_w (+ optional extra partials), then either the raw XYZZ partial
+// (multi-GPU: partials are gathered and combined later) or the normalised affine image.
+template <int CURVE>
+__global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, uint32_t c,
+                         const xyzz_t *__restrict__ extra, uint32_t n_extra, int normalise,
+                         xyzz_t *__restrict__ out_partial, affine_t *__restrict__ out_affine,
+                         uint32_t *__restrict__ out_inf) {
+    using Cv = Curve<CURVE>;
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    xyzz_t acc = Cv::identity();
+    for (int w = (int)nwin - 1; w >= 0; w--) {
+        if (!Cv::is_identity(acc)) for (uint32_t b = 0; b < c; b++) acc = Cv::dbl(acc);
+        xyzz_t s = load_xyzz(window_sums + w);
+        Cv::add(acc, s);
+    }
+    for (uint32_t i = 0; i < n_extra; i++) { xyzz_t s = load_xyzz(extra + i); Cv::add(acc, s); }
+    if (out_partial) store_xyzz(out_partial, acc);
+    if (normalise) {
+        affine_t a; uint32_t inf;
+        Cv::to_affine(acc, a, inf);
+        store_fe(&out_affine->x, a.x); store_fe(&out_affine->y, a.y);
+        *out_inf = inf;
+    }
+}
+
+}  // namespace accmsm

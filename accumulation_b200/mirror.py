@@ -1,0 +1,134 @@
+"""Reference-named harness mirror of the calls that reach the hot path.
+
+Same names, argument meaning and accept/reject behaviour as the reference's call sites, so the parity
+tests read like the reference's own; everything computes on the GPU through the C-ABI.  The C++ twin of
+this file, used by the Rust-side integration, is `accumulation_b200/host/ark_mirror.hpp`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+
+@dataclass
+class CommitterKey:
+    """trivial_pc::CommitterKey{generators, hiding_generator} / ipa_pc::CommitterKey{comm_key, h, s}.
+
+    The hiding generator is registered as the base after the last generator so that
+    `commit(elems, randomizer)` is a single device MSM."""
+    bases: "object"          # accumulation_b200.Bases: generators || hiding_generator
+    num_generators: int
+
+    @staticmethod
+    def new(ctx, curve: int, generators_xy, hiding_generator_xy=None) -> "CommitterKey":
+        gens = np.ascontiguousarray(generators_xy, dtype=np.uint64).reshape(-1, 8)
+        allb = gens if hiding_generator_xy is None else np.concatenate(
+            [gens, np.ascontiguousarray(hiding_generator_xy, dtype=np.uint64).reshape(1, 8)])
+        return CommitterKey(ctx.register_bases(curve, allb), gens.shape[0])
+
+    def supported_num_elems(self) -> int:   # src/hp_as/mod.rs:129,681
+        return self.num_generators
+
+    @property
+    def curve(self) -> int:
+        return self.bases.curve
+
+
+class PedersenCommitment:
+    """ark_poly_commit::trivial_pc::PedersenCommitment (call sites: src/hp_as/mod.rs:196,197,214,377,910-918;
+    src/r1cs_nark_as/r1cs_nark/mod.rs:216-261,375-407; src/r1cs_nark_as/mod.rs:394-410,1081-1097)."""
+
+    @staticmethod
+    def commit(ck: CommitterKey, elems, randomizer=None):
+        """-> (xy[8], infinity).  ark-ec truncates to min(len(generators), len(elems))."""
+        el = np.ascontiguousarray(elems, dtype=np.uint64).reshape(-1, 4)[: ck.num_generators]
+        ctx = ck.bases.ctx
+        if randomizer is None:
+            return ctx.msm(ck.bases, el, montgomery=True)
+        return ctx.commit(ck.bases, el, hiding_index=ck.num_generators, randomizer_mont=randomizer)
+
+
+class SuccinctCheckPolynomial:
+    """ark_poly_commit::ipa_pc::SuccinctCheckPolynomial(pub Vec<F>) (src/ipa_pc_as/mod.rs:245,400,418)."""
+
+    def __init__(self, ctx, field: int, challenges):
+        self.ctx, self.field = ctx, field
+        self.challenges = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)
+
+    def compute_coeffs(self):
+        return self.ctx.compute_coeffs(self.field, self.challenges)
+
+
+class InnerProductArgPC:
+    """The parts of ark_poly_commit::ipa_pc::InnerProductArgPC that run the MSM."""
+
+    @staticmethod
+    def cm_commit(comm_key: CommitterKey, scalars, hiding_generator_index: Optional[int] = None, randomizer=None):
+        if randomizer is None:
+            return PedersenCommitment.commit(comm_key, scalars)
+        el = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)[: comm_key.num_generators]
+        idx = comm_key.num_generators if hiding_generator_index is None else hiding_generator_index
+        return comm_key.bases.ctx.commit(comm_key.bases, el, hiding_index=idx, randomizer_mont=randomizer)
+
+    @staticmethod
+    def check_final_key(vk: CommitterKey, check_poly_challenges, final_comm_key_xy, final_comm_key_inf: int = 0) -> bool:
+        """Tail of check_individual_opening_challenges (reached from decide, src/ipa_pc_as/mod.rs:836-845):
+        final_key = cm_commit(vk.comm_key, h.compute_coeffs()); accept iff final_key == proof.final_comm_key."""
+        ok, _, _ = vk.bases.ctx.ipa_check_final_key(vk.bases, check_poly_challenges, final_comm_key_xy, final_comm_key_inf)
+        return ok
+
+
+def matrix_vec_mul(ctx, field: int, matrices, inp, wit):
+    """r1cs_nark::matrix_vec_mul for A, B, C in one launch (src/r1cs_nark_as/r1cs_nark/mod.rs:443-447)."""
+    return ctx.csr_matvec(field, matrices, inp, wit)
+
+
+class ASForHadamardProducts:
+    """Vector / commitment steps of src/hp_as/mod.rs that sit on the hot path."""
+
+    @staticmethod
+    def compute_hp(ctx, field, a_vec, b_vec):                       # :278-285
+        return ctx.hadamard(field, a_vec, b_vec)
+
+    @staticmethod
+    def compute_t_vecs(ctx, field, a_vecs, b_vecs, mu_challenges, hp_vec_len, hiding_vecs=None):   # :288-349
+        ha, hb = hiding_vecs if hiding_vecs is not None else (None, None)
+        return ctx.tvecs(field, a_vecs, b_vecs, mu_challenges, hp_vec_len, ha, hb)
+
+    @staticmethod
+    def combine_vectors(ctx, field, vectors, challenges, hiding_vecs=None):   # :492-512
+        return ctx.lincomb(field, vectors, challenges, hiding_vecs)
+
+    @staticmethod
+    def scale_vector(ctx, field, vector, coeff):                    # :482-489
+        return ctx.scale(field, vector, coeff)
+
+    @staticmethod
+    def compute_product_poly_comm(ck: CommitterKey, t_vecs) -> tuple:   # :354-388
+        """(low, high): commitments to every t-vector except the middle one, without randomiser."""
+        n2 = len(t_vecs)
+        mid = (n2 - 1) // 2
+        low = [PedersenCommitment.commit(ck, t_vecs[i]) for i in range(mid)]
+        high = [PedersenCommitment.commit(ck, t_vecs[i]) for i in range(mid + 1, n2)]
+        return low, high
+
+    @staticmethod
+    def decide(ck: CommitterKey, instance, witness) -> bool:        # :894-925
+        """instance = (comm_1, comm_2, comm_3) as (xy, inf) pairs; witness = (a_vec, b_vec, randomness|None),
+        randomness = (rand_1, rand_2, rand_3)."""
+        from . import scalar_field
+        ctx = ck.bases.ctx
+        a_vec, b_vec, rand = witness
+        field = scalar_field(ck.curve)
+        product = ASForHadamardProducts.compute_hp(ctx, field, a_vec, b_vec)
+        r = rand if rand is not None else (None, None, None)
+        tests = [PedersenCommitment.commit(ck, a_vec, r[0]), PedersenCommitment.commit(ck, b_vec, r[1]),
+                 PedersenCommitment.commit(ck, product, r[2])]
+        for (got_xy, got_inf), (exp_xy, exp_inf) in zip(tests, instance):
+            if got_inf != int(exp_inf):
+                return False
+            if not got_inf and not np.array_equal(got_xy, np.asarray(exp_xy, dtype=np.uint64)):
+                return False
+        return True

@@ -1,0 +1,146 @@
+/* accmsm -- C-ABI of the B200-native commitment / MSM hot path for arkworks-rs/accumulation.
+ *
+ * Drop-in boundary: the reference crate forbids `unsafe` (src/lib.rs:24) and never calls
+ * an MSM itself; every MSM is reached through ark-poly-commit (`PedersenCommitment::commit`,
+ * `InnerProductArgPC::{commit, check_individual_opening_challenges}`), which call
+ * `ark_ec::msm::VariableBaseMSM::multi_scalar_mul`.  A Rust `accmsm-sys` crate binds exactly the
+ * entry points below (INTEGRATION.md shows the stub) and a `[patch]` of ark-poly-commit routes those
+ * bodies here.  Plain pointers and sizes only; no allocation crosses the boundary.
+ *
+ * Data formats (identical to the ark-ff / ark-ec 0.2 memory images):
+ *   field element : 4 x uint64_t little-endian limbs; "mont" = Fp256 Montgomery image (R = 2^256),
+ *                   "canon" = BigInteger256 canonical integer
+ *   affine point  : 8 x uint64_t = x[4] || y[4] (Montgomery) + a separate infinity byte; the identity
+ *                   is written as (0, 1, infinity = 1) exactly like ark-ec's GroupAffine::zero()
+ *   curve id      : 0 = Pallas (coordinates Fp, scalars Fq), 1 = Vesta (coordinates Fq, scalars Fp)
+ *   field id      : 0 = Fp (Pallas base), 1 = Fq (Pallas scalar)
+ *
+ * Every call is blocking and returns 0 or a negative ACCMSM_E_* code; nothing throws or aborts.
+ * There is no CPU fallback: without a CUDA device accmsm_init fails with ACCMSM_E_CUDA.
+ * A ctx is bound to one GPU and serialises its calls internally (one ctx per GPU per process).
+ */
+#ifndef ACCMSM_H
+#define ACCMSM_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct accmsm_ctx accmsm_ctx;
+
+enum {
+    ACCMSM_OK = 0,
+    ACCMSM_E_CUDA = -1,      /* CUDA runtime error (accmsm_last_error has the text) */
+    ACCMSM_E_ARG = -2,       /* bad argument (null pointer, bad curve/field id, range) */
+    ACCMSM_E_HANDLE = -3,    /* unknown or released bases handle */
+    ACCMSM_E_NOMEM = -4      /* device or pinned allocation failed */
+};
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int  accmsm_init(accmsm_ctx **out, int device);
+void accmsm_destroy(accmsm_ctx *ctx);
+const char *accmsm_strerror(int code);
+const char *accmsm_last_error(accmsm_ctx *ctx);
+/* tuning knobs (0 = automatic): window bits c for the next MSMs */
+int  accmsm_set_window_bits(accmsm_ctx *ctx, int c);
+/* number of this library's kernels launched by ctx so far (bench.py reports it as gpu_launches) */
+uint64_t accmsm_kernel_launches(accmsm_ctx *ctx);
+/* CUDA-event time of the last call's device work, split by stage (ms); names in accmsm_stage_name */
+int  accmsm_last_timings(accmsm_ctx *ctx, float *ms_out, int max_stages);
+const char *accmsm_stage_name(int stage);
+
+/* ---- commitment keys ------------------------------------------------------------------------------
+ * Replaces holding `ck.generators` / `comm_key` on the host: the key is registered once (trim / index
+ * time: src/ipa_pc_as/mod.rs:507-513, src/hp_as/mod.rs:640-641) and stays resident in HBM.
+ * xy: n x 8 u64.  infinity: n bytes or NULL (generators are never the identity; identity bases are
+ * accepted and contribute nothing, like ark-ec's add_assign_mixed). */
+int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const uint8_t *infinity,
+                          size_t n, uint64_t *handle);
+int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle);
+
+/* ---- MSM ------------------------------------------------------------------------------------------
+ * ark_ec::msm::VariableBaseMSM::multi_scalar_mul(&bases[offset..offset+n], &scalars[..n]) followed by
+ * into_affine().  scalars: HOST pointer, n x 4 u64; scalars_montgomery = 1 takes the Fp256 image that
+ * PedersenCommitment::commit / cm_commit receive (into_repr() happens on the device), 0 takes
+ * BigInteger256.  n = 0 returns the identity.  ark-ec truncates to min(len): the caller passes that. */
+int accmsm_msm(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const uint64_t *scalars,
+               int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf);
+/* k scalar vectors over the same bases (hp_as::decide commits a, b, a∘b: src/hp_as/mod.rs:910-918;
+ * NARK prove commits z_A, z_B, z_C: src/r1cs_nark_as/r1cs_nark/mod.rs:216-218).
+ * scalars: k x n x 4 u64, out_xy: k x 8, out_inf: k. */
+int accmsm_msm_batch(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k,
+                     const uint64_t *scalars, int scalars_montgomery, uint64_t *out_xy, uint8_t *out_inf);
+/* PedersenCommitment::commit(ck, elems, randomizer) / IpaPC::cm_commit(key, scalars, hiding, rand)
+ * (SURVEY.md App. A.2): MSM over the first n generators plus randomizer * hiding generator, where the
+ * hiding generator is the registered base at index hiding_index.  randomizer_mont may be NULL. */
+int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *elems_mont,
+                  size_t hiding_index, const uint64_t *randomizer_mont, uint64_t out_xy[8],
+                  uint8_t *out_inf);
+
+/* Device-resident variants for the multi-GPU path (one process per GPU): d_scalars is a
+ * DEVICE pointer on ctx's GPU, the result is the un-normalised partial sum written to DEVICE memory
+ * (16 x u64: X, Y, ZZ, ZZZ), `stream` is a cudaStream_t (NULL = the ctx stream; the call is then
+ * synchronous, otherwise it only enqueues). */
+int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n,
+                           const void *d_scalars, int scalars_montgomery, void *d_out_partial,
+                           void *stream);
+/* Sum k gathered partials (DEVICE, k x 16 u64) and normalise: the G-way add after the NCCL gather. */
+int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k,
+                                uint64_t out_xy[8], uint8_t *out_inf);
+
+/* ---- IPA decider tail (K3 fused into K2) --------------------------------------------------------------
+ * IpaPC::check_individual_opening_challenges after succinct_check (reached from
+ * AtomicASForInnerProductArgPC::decide, src/ipa_pc_as/mod.rs:836-845):
+ *   final_key = cm_commit(comm_key, h.compute_coeffs())     with h = SuccinctCheckPolynomial(challenges)
+ * The 2^k coefficients are generated on the device inside the digit-decomposition kernel and never
+ * touch HBM.  challenges_mont: k x 4 u64, xi_1 first.  The key must hold >= 2^k bases. */
+int accmsm_ipa_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k,
+                         uint64_t out_xy[8], uint8_t *out_inf);
+/* accept iff final_key == proof.final_comm_key (affine equality); *accept = 0/1 */
+int accmsm_ipa_check_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k,
+                               const uint64_t expected_xy[8], uint8_t expected_inf, int *accept,
+                               uint64_t out_xy[8], uint8_t *out_inf);
+/* slice [coeff_offset, coeff_offset + n) of the coefficient vector against bases [0, n) of `handle`
+ * (a GPU that owns key[coeff_offset ..] registers just that slice); partial stays on the device */
+int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont,
+                                     int k, size_t coeff_offset, size_t n, void *d_out_partial,
+                                     void *stream);
+
+/* ---- field-vector kernels (K3 materialised, K4, K5); all pointers HOST, Montgomery images -------------- */
+/* SuccinctCheckPolynomial::compute_coeffs (src/ipa_pc_as/mod.rs:400): out = 2^k elements */
+int accmsm_compute_coeffs(accmsm_ctx *ctx, int field, const uint64_t *challenges_mont, int k, uint64_t *out);
+/* combine_succinct_check_polynomials (src/ipa_pc_as/mod.rs:391-404):
+ * out[j] = random_poly[j] (if j < n_random) + sum_i alphas[i] * coeffs_i[j];  challenges: m x k x 4 */
+int accmsm_combine_check_polys(accmsm_ctx *ctx, int field, const uint64_t *challenges_mont, int m, int k,
+                               const uint64_t *alphas_mont, const uint64_t *random_poly_mont,
+                               size_t n_random, uint64_t *out);
+/* DensePolynomial::evaluate (src/ipa_pc_as/mod.rs:439) */
+int accmsm_poly_evaluate(accmsm_ctx *ctx, int field, const uint64_t *coeffs_mont, size_t n,
+                         const uint64_t *point_mont, uint64_t out[4]);
+/* compute_hp (src/hp_as/mod.rs:278-285) */
+int accmsm_vec_hadamard(accmsm_ctx *ctx, int field, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
+/* scale_vector (src/hp_as/mod.rs:482-489) */
+int accmsm_vec_scale(accmsm_ctx *ctx, int field, const uint64_t *v, size_t n, const uint64_t *coeff, uint64_t *out);
+/* combine_vectors (src/hp_as/mod.rs:492-512): out[li] = hiding[li] + sum_ni ch[ni] * vecs[ni][li];
+ * ragged: vecs[ni] has lens[ni] elements, out has max(lens, n_hiding) elements (out_len receives it) */
+int accmsm_vec_lincomb(accmsm_ctx *ctx, int field, const uint64_t *const *vecs, const size_t *lens, int m,
+                       const uint64_t *challenges, const uint64_t *hiding, size_t n_hiding,
+                       uint64_t *out, size_t out_capacity, size_t *out_len);
+/* compute_t_vecs (src/hp_as/mod.rs:288-349): n inputs, mu has n (+1 with hiding) entries,
+ * out = (2n-1) x len row-major */
+int accmsm_vec_tvecs(accmsm_ctx *ctx, int field, const uint64_t *const *a_vecs, const size_t *a_lens,
+                     const uint64_t *const *b_vecs, const size_t *b_lens, int n, const uint64_t *mu,
+                     size_t len, const uint64_t *hiding_a, size_t n_ha, const uint64_t *hiding_b,
+                     size_t n_hb, uint64_t *out);
+/* matrix_vec_mul (src/r1cs_nark_as/r1cs_nark/mod.rs:443-462) for up to 3 CSR matrices sharing z =
+ * input || witness in one launch: out[m] = n_rows x 4 u64 */
+int accmsm_csr_matvec(accmsm_ctx *ctx, int field, int n_mats, const uint32_t *const *row_ptr,
+                      const uint32_t *const *cols, const uint64_t *const *coeffs_mont, size_t n_rows,
+                      const uint64_t *input, size_t n_input, const uint64_t *witness, size_t n_witness,
+                      uint64_t *const *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -26,3 +26,23 @@ template <int F> static void binop(int op, const uint32_t *a, const uint32_t *b,
 extern "C" void host_fe_op(int field, int op, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n) {
     if (field == 0) binop<0>(op, a, b, o, n); else binop<1>(op, a, b, o, n);
 }
+
+#include "../../accumulation_b200/csrc/ec.cuh"
+template <int C> static void ec_sum(const uint32_t *xy, const uint8_t *neg, size_t n, int mode, uint32_t *out_xy, uint8_t *out_inf) {
+    using Cv = Curve<C>;
+    xyzz_t acc = Cv::identity(), acc2 = Cv::identity();
+    for (size_t i = 0; i < n; i++) {
+        affine_t p; memcpy(&p, xy + 16 * i, 64);
+        if (neg && neg[i]) p = Cv::neg(p);
+        if (mode == 0) Cv::madd(acc, p);                       // mixed adds
+        else if (mode == 1) { xyzz_t q = Cv::from_affine(p); Cv::add(acc, q); }   // full adds
+        else { if (i & 1) Cv::madd(acc2, p); else Cv::madd(acc, p); }             // two partials, then merged
+    }
+    if (mode == 2) Cv::add(acc, acc2);
+    if (mode == 3) { acc = Cv::identity(); affine_t p; memcpy(&p, xy, 64); Cv::madd(acc, p); for (size_t i = 0; i < n; i++) acc = Cv::dbl(acc); }
+    affine_t o; uint32_t inf; Cv::to_affine(acc, o, inf);
+    memcpy(out_xy, &o, 64); *out_inf = (uint8_t)inf;
+}
+extern "C" void host_ec_sum(int curve, const uint32_t *xy, const uint8_t *neg, size_t n, int mode, uint32_t *out_xy, uint8_t *out_inf) {
+    if (curve == 0) ec_sum<0>(xy, neg, n, mode, out_xy, out_inf); else ec_sum<1>(xy, neg, n, mode, out_xy, out_inf);
+}
