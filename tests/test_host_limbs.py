@@ -1,0 +1,86 @@
+"""CPU suite: the device headers (fp.cuh / ec.cuh) compiled for the HOST with an emulated carry flag
+(tests/host/host_shim.cpp) must agree limb-for-limb with the oracle.  This checks the 8x32-bit Montgomery
+multiplier and the XYZZ group law without a GPU; it is test scaffolding, never part of libaccmsm.so."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cref, pyref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host", "host_shim.cpp")
+SO = os.path.join(HERE, "host", "libhostshim.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    deps = [SRC, os.path.join(HERE, "..", "accumulation_b200", "csrc", "fp.cuh"), os.path.join(HERE, "..", "accumulation_b200", "csrc", "ec.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO, SRC])
+    return C.CDLL(SO)
+
+
+def fe_op(lib, field, code, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    bp = None if b is None else np.ascontiguousarray(b, dtype=np.uint64).ctypes.data_as(C.c_void_p)
+    lib.host_fe_op(C.c_int(field), C.c_int(code), a.ctypes.data_as(C.c_void_p), bp, out.ctypes.data_as(C.c_void_p), C.c_size_t(a.size // 4))
+    return out
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_field_limb_algorithms(shim, field):
+    m = [pyref.P_PALLAS_BASE, pyref.Q_PALLAS_SCALAR][field]
+    n = 20000
+    a = cref.gen_scalars(field, 1, n, True)
+    b = cref.gen_scalars(field, 2, n, True)
+    edge = cref.ints_to_arr([0, 1, m - 1, (1 << 256) % m, m - 2, 2, (1 << 255) % m, 0xffffffff, 1 << 32, m >> 1,
+                             (1 << 254) - 1, (1 << 224), m - (1 << 32)])
+    ea, eb = np.repeat(edge, len(edge), axis=0), np.tile(edge, (len(edge), 1))
+    a, b = np.concatenate([a, ea]), np.concatenate([b, eb])
+    assert (fe_op(shim, field, 0, a, b) == cref.fe_mul(field, a, b)).all()
+    assert (fe_op(shim, field, 1, a, b) == cref.fe_add(field, a, b)).all()
+    assert (fe_op(shim, field, 2, a, b) == cref.fe_sub(field, a, b)).all()
+    assert (fe_op(shim, field, 3, a) == cref.fe_mul(field, a, a)).all()
+    assert (fe_op(shim, field, 5, a) == cref.from_mont(field, a)).all()
+    assert (fe_op(shim, field, 6, a) == cref.to_mont(field, a)).all()
+    assert (fe_op(shim, field, 7, a) == cref.fe_sub(field, np.zeros_like(a), a)).all()
+    assert (fe_op(shim, field, 4, a[:200]) == cref.fe_inv(field, a[:200])).all()
+    assert (fe_op(shim, field, 4, ea) == cref.fe_inv(field, ea)).all()
+
+
+def ec_sum(lib, curve, pts, neg, mode):
+    pts = np.ascontiguousarray(pts, dtype=np.uint64)
+    out = np.empty(8, dtype=np.uint64)
+    inf = C.c_uint8(0)
+    negp = None if neg is None else np.ascontiguousarray(neg, dtype=np.uint8).ctypes.data_as(C.c_void_p)
+    lib.host_ec_sum(C.c_int(curve), pts.ctypes.data_as(C.c_void_p), negp, C.c_size_t(pts.shape[0]), C.c_int(mode),
+                    out.ctypes.data_as(C.c_void_p), C.byref(inf))
+    return out, inf.value
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_xyzz_group_law(shim, curve):
+    sm = pyref.scalar_modulus(curve)
+    n = 60
+    pts = cref.gen_points(curve, 3 + curve, n)
+    neg = (np.arange(n) % 3 == 0).astype(np.uint8)
+    sc = np.array([cref.from_int(sm - 1) if neg[i] else cref.from_int(1) for i in range(n)])
+    exp, einf = cref.msm_ark(curve, pts, sc)
+    for mode in (0, 1, 2):   # mixed adds, full adds, two partials merged
+        got, ginf = ec_sum(shim, curve, pts, neg, mode)
+        assert ginf == einf and (got == exp).all()
+    P, Qp = pts[:1], pts[1:2]
+    # the exceptional cases the reference's fixtures hit: P+P, P-P, P+P+P, (P-P)+Q, 2P-2P
+    for seq, negs, scal in [([P, P], [0, 0], [2, 0]), ([P, P], [0, 1], [0, 0]), ([P, P, P], [0, 0, 0], [3, 0]),
+                            ([P, P, Qp], [0, 1, 0], [0, 1]), ([P, P, P, P], [0, 0, 1, 1], [0, 0])]:
+        exp, einf = cref.msm_ark(curve, np.concatenate([P, Qp]), cref.ints_to_arr(scal))
+        for mode in (0, 1, 2):
+            got, ginf = ec_sum(shim, curve, np.concatenate(seq), np.array(negs, dtype=np.uint8), mode)
+            assert ginf == einf and (got == exp).all()      # identity image is (0, R, inf = 1)
+    got, ginf = ec_sum(shim, curve, np.repeat(P, 20, axis=0), None, 3)   # 20 doublings of P
+    exp, einf = cref.point_mul(curve, P[0], 0, cref.from_int(1 << 20))
+    assert ginf == 0 and (got == exp).all()
