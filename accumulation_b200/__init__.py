@@ -83,6 +83,19 @@ class Context:
                                                     C.byref(h)), "register_bases")
         return Bases(self, curve, int(h.value), xy.shape[0])
 
+    def register_synthetic_bases(self, curve: int, seed: int, n: int, first_index: int = 0) -> "Bases":
+        h = C.c_uint64(0)
+        self._check(self._lib.accmsm_register_synthetic_bases(self._h, C.c_int(curve), C.c_uint64(seed), C.c_uint64(first_index),
+                                                              C.c_size_t(n), C.byref(h)), "register_synthetic_bases")
+        return Bases(self, curve, int(h.value), n)
+
+    def download_bases(self, bases: "Bases", offset: int = 0, n: Optional[int] = None):
+        n = bases.n - offset if n is None else n
+        out = np.empty((n, 8), dtype=np.uint64)
+        self._check(self._lib.accmsm_download_bases(self._h, C.c_uint64(bases.handle), C.c_size_t(offset), C.c_size_t(n), _p(out)),
+                    "download_bases")
+        return out
+
     # ---- MSM
     def msm(self, bases: "Bases", scalars, montgomery: bool = True, offset: int = 0, n: Optional[int] = None):
         sc = _u64(scalars).reshape(-1, 4)
@@ -119,17 +132,26 @@ class Context:
                                             C.c_size_t(hiding_index), _p(r), _p(out), C.byref(inf)), "commit")
         return out, int(inf.value)
 
+    def msm_dev(self, bases: "Bases", d_scalars_ptr: int, n: int, montgomery: bool = True, offset: int = 0, stream: int = 0):
+        """MSM of scalars already resident in HBM (device pointer); blocks until the affine result is on the host."""
+        out = np.empty(8, dtype=np.uint64)
+        inf = C.c_uint8(0)
+        self._check(self._lib.accmsm_msm_dev(self._h, C.c_uint64(bases.handle), C.c_size_t(offset), C.c_size_t(n),
+                                             C.c_void_p(d_scalars_ptr), C.c_int(int(montgomery)), _p(out), C.byref(inf),
+                                             C.c_void_p(stream)), "msm_dev")
+        return out, int(inf.value)
+
     def msm_partial_dev(self, bases: "Bases", d_scalars_ptr: int, n: int, d_out_ptr: int, montgomery: bool = True,
                         offset: int = 0, stream: int = 0):
         self._check(self._lib.accmsm_msm_partial_dev(self._h, C.c_uint64(bases.handle), C.c_size_t(offset), C.c_size_t(n),
                                                      C.c_void_p(d_scalars_ptr), C.c_int(int(montgomery)),
                                                      C.c_void_p(d_out_ptr), C.c_void_p(stream)), "msm_partial_dev")
 
-    def combine_partials_dev(self, curve: int, d_partials_ptr: int, k: int):
+    def combine_partials_dev(self, curve: int, d_partials_ptr: int, k: int, stream: int = 0):
         out = np.empty(8, dtype=np.uint64)
         inf = C.c_uint8(0)
         self._check(self._lib.accmsm_combine_partials_dev(self._h, C.c_int(curve), C.c_void_p(d_partials_ptr), C.c_size_t(k),
-                                                          _p(out), C.byref(inf)), "combine_partials_dev")
+                                                          _p(out), C.byref(inf), C.c_void_p(stream)), "combine_partials_dev")
         return out, int(inf.value)
 
     # ---- IPA decider tail

@@ -17,8 +17,8 @@ using namespace accmsm;
 
 namespace {
 
-enum Stage { ST_H2D = 0, ST_DIGITS, ST_SCAN, ST_SCATTER, ST_ACCUMULATE, ST_REDUCE, ST_FINISH, ST_D2H, ST_COUNT };
-const char *STAGE_NAMES[ST_COUNT] = {"h2d", "digits", "scan", "scatter", "accumulate", "bucket_reduce", "finish", "d2h"};
+enum Stage { ST_H2D = 0, ST_DIGITS, ST_SCAN, ST_SCATTER, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_FINISH, ST_D2H, ST_COUNT };
+const char *STAGE_NAMES[ST_COUNT] = {"h2d", "digits", "scan", "scatter", "accumulate", "fixup", "bucket_reduce", "finish", "d2h"};
 
 struct Bases {
     int curve = 0;
@@ -100,6 +100,7 @@ void collect_timings(accmsm_ctx *ctx) {
         if (prev >= 0) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ctx->ev[prev], ctx->ev[i]) == cudaSuccess) ctx->timings[prev] = ms;
+            else (void)cudaGetLastError();   // not ready yet: leave the slot, clear the non-sticky error
         }
         prev = i;
     }
@@ -167,6 +168,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
         k_accumulate<CURVE><<<grid, ACC_THREADS, smem, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p,
                                                               B.d_xy + offset, ctx->buckets.p,
                                                               ctx->cta_ids.p, ctx->cta_parts.p);
+        mark(ctx, ST_FIXUP, st);
         uint32_t ns = 2 * grid;
         size_t smem2 = ns * (sizeof(xyzz_t) + sizeof(uint32_t));
         k_fixup<CURVE><<<1, FIX_THREADS, smem2, st>>>(ctx->cta_ids.p, ctx->cta_parts.p, ns, ctx->buckets.p);
@@ -351,6 +353,9 @@ uint64_t accmsm_kernel_launches(accmsm_ctx *ctx) { return ctx ? ctx->launches : 
 int accmsm_last_timings(accmsm_ctx *ctx, float *ms_out, int max_stages) {
     if (!ctx || !ms_out) return ACCMSM_E_ARG;
     int k = std::min<int>(max_stages, ST_COUNT);
+    // calls that only enqueued on a caller stream are collected here, once the caller has synchronised
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    collect_timings(ctx);
     for (int i = 0; i < k; i++) ms_out[i] = ctx->timings[i];
     return k;
 }
@@ -374,6 +379,40 @@ int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const 
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     *handle = ctx->next_handle++;
     ctx->bases[*handle] = B;
+    return ACCMSM_OK;
+}
+
+int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, uint64_t first_index, size_t n,
+                                    uint64_t *handle) {
+    if (!ctx || !handle || (curve != 0 && curve != 1)) return fail_arg(ctx, "register_synthetic_bases: bad argument");
+    if (n >= (size_t(1) << 31)) return fail_arg(ctx, "register_synthetic_bases: n must be < 2^31");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Bases B;
+    B.curve = curve; B.n = n;
+    CU(ctx, cudaMalloc(&B.d_xy, std::max<size_t>(n, 1) * sizeof(affine_t)));
+    if (n) {
+        uint32_t blocks = (uint32_t)((n + 127) / 128);
+        if (curve == 0) k_synth_points<0><<<blocks, 128, 0, ctx->stream>>>(seed, first_index, (uint32_t)n, B.d_xy);
+        else k_synth_points<1><<<blocks, 128, 0, ctx->stream>>>(seed, first_index, (uint32_t)n, B.d_xy);
+        ctx->launches++;
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(B.d_xy); CU(ctx, e); }
+    }
+    *handle = ctx->next_handle++;
+    ctx->bases[*handle] = B;
+    return ACCMSM_OK;
+}
+
+int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out) {
+    if (!ctx || (n && !xy_out)) return fail_arg(ctx, "download_bases: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "download_bases: range exceeds registered bases");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n) CU(ctx, cudaMemcpyAsync(xy_out, B->d_xy + offset, n * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return ACCMSM_OK;
 }
 
@@ -441,6 +480,25 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
     return msm_host_scalars(ctx, *B, 0, n, elems_mont, 1, ctx->partial.p, 1, out_xy, out_inf);
 }
 
+int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
+                   int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf, void *stream) {
+    if (!ctx || !out_xy || !out_inf || (n && !d_scalars)) return fail_arg(ctx, "msm_dev: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "msm_dev: range exceeds registered bases");
+    if (n == 0) return write_identity(ctx, B->curve, out_xy, out_inf);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    clear_marks(ctx);
+    const uint8_t *d_inf = B->d_inf ? B->d_inf + offset : nullptr;
+    int rc;
+    if (B->curve == 0) { MemScalars<1> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<0>(ctx, *B, offset, n, src, d_inf, nullptr, 0, nullptr, true, st); }
+    else { MemScalars<0> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<1>(ctx, *B, offset, n, src, d_inf, nullptr, 0, nullptr, true, st); }
+    if (rc) return rc;
+    return fetch_affine(ctx, out_xy, out_inf, st);
+}
+
 int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
                            int scalars_montgomery, void *d_out_partial, void *stream) {
     if (!ctx || !d_out_partial || (n && !d_scalars)) return fail_arg(ctx, "msm_partial_dev: bad argument");
@@ -469,12 +527,12 @@ int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size
 }
 
 int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k, uint64_t out_xy[8],
-                                uint8_t *out_inf) {
+                                uint8_t *out_inf, void *stream) {
     if (!ctx || !out_xy || !out_inf || (k && !d_partials) || (curve != 0 && curve != 1)) return fail_arg(ctx, "combine_partials: bad argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    clear_marks(ctx);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    // stage marks of a preceding accmsm_*_partial_dev on the same stream are kept (bench.py reads them)
     mark(ctx, ST_FINISH, st);
     if (curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
     else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
@@ -485,7 +543,7 @@ int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partia
 static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_mont, int k, size_t coeff_offset, size_t n,
                    xyzz_t *d_partial, bool normalise, cudaStream_t st) {
     CU(ctx, ctx->misc.ensure(64 * 32));
-    CU(ctx, cudaMemcpyAsync(ctx->misc.p, challenges_mont, (size_t)k * 32, cudaMemcpyHostToDevice, st));
+    if (k) CU(ctx, cudaMemcpyAsync(ctx->misc.p, challenges_mont, (size_t)k * 32, cudaMemcpyHostToDevice, st));
     if (B.curve == 0) { IpaScalars<1> src{ctx->misc.p, k, (uint32_t)coeff_offset}; return run_msm<0>(ctx, B, 0, n, src, B.d_inf, nullptr, 0, d_partial, normalise, st); }
     IpaScalars<0> src{ctx->misc.p, k, (uint32_t)coeff_offset};
     return run_msm<1>(ctx, B, 0, n, src, B.d_inf, nullptr, 0, d_partial, normalise, st);
@@ -493,7 +551,7 @@ static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_m
 
 int accmsm_ipa_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k, uint64_t out_xy[8],
                          uint8_t *out_inf) {
-    if (!ctx || !out_xy || !out_inf || !challenges_mont || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key: bad argument");
+    if (!ctx || !out_xy || !out_inf || (k && !challenges_mont) || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key: bad argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
@@ -523,7 +581,7 @@ int accmsm_ipa_check_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t 
 
 int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k,
                                      size_t coeff_offset, size_t n, void *d_out_partial, void *stream) {
-    if (!ctx || !d_out_partial || !challenges_mont || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key_partial_dev: bad argument");
+    if (!ctx || !d_out_partial || (k && !challenges_mont) || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key_partial_dev: bad argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;

@@ -441,4 +441,44 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_synth_points: seeded synthetic commitment key for benchmarks / tests: base i is
+// s_i * G with G = (-1, 2) and s_i a 254-bit SplitMix64 value of (seed, global index), so any shard of
+// the key can be generated independently on its own GPU without a host round trip.
+// ------------------------------------------------------------------------------------------------
+ACC_D uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_synth_points(uint64_t seed, uint64_t first_index, uint32_t n,
+                                                       affine_t *__restrict__ out) {
+    using Cv = Curve<CURVE>;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t idx = first_index + i;
+    uint32_t s[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint64_t v = splitmix64(seed ^ splitmix64(idx * 4 + j));
+        s[2 * j] = (uint32_t)v; s[2 * j + 1] = (uint32_t)(v >> 32);
+    }
+    s[7] &= 0x3fffffffu;    // < 2^254 < group order
+    s[0] |= 1u;             // never zero
+    affine_t g;
+    g.x = Cv::F::neg(Cv::F::one());
+    g.y = Cv::F::dbl(Cv::F::one());
+    xyzz_t acc = Cv::identity();
+#pragma unroll 1
+    for (int b = 253; b >= 0; b--) {
+        acc = Cv::dbl(acc);
+        if ((s[b >> 5] >> (b & 31)) & 1u) Cv::madd(acc, g);
+    }
+    affine_t a; uint32_t inf;
+    Cv::to_affine(acc, a, inf);
+    store_fe(&out[i].x, a.x); store_fe(&out[i].y, a.y);
+}
+
 }  // namespace accmsm

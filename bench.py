@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json headline: Pallas variable-base MSM throughput (Mpts/s) at 2^20 points per GPU,
+plus the ipa-pc-as decide tail (fused h(X) -> commitment-key MSM) in ms at degree 2^18 / 2^20.
+
+One process per GPU (torchrun).  A "step" is ONE MSM over the whole (sharded) key: every rank runs the
+Pippenger pipeline on its contiguous point range, one 128-byte XYZZ partial per rank is all-gathered over
+NCCL, rank 0 adds them and normalises.  Weak scaling: 2^20 points per GPU, so the job at N
+GPUs is a single N * 2^20-point MSM (config 5 of BASELINE.json sweeps 2^12 .. 2^24).
+
+  value : Mpts/s with scalars already resident in HBM (device-timed, CUDA events per step, L2 flushed
+          between steps, max over ranks)
+  e2e   : same metric through the host-buffer path: pinned host scalars -> H2D -> MSM -> affine point D2H
+  --impl reference : the CPU restatement of ark-ec 0.2 VariableBaseMSM (oracle/, OpenMP over windows like
+          ark's rayon path) on the box's host cores -- the reference itself is Rust and cannot be built here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+LOG_N_PER_GPU = 20
+SEED = 0xACC5
+FE_MUL_PEAK_G = 74.9          # measured on this pool's B200 (tools/ubench.cu, profiles/r01_ubench_first.jsonl), Gmul/s
+MULS_PER_MADD = 10            # XYZZ madd-2008-s: 8M + 2S
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def rand_scalars(n, seed):
+    """uniform 254-bit values (< both moduli; the moduli are 2^254 + ~2^125): valid canonical integers and valid
+    Fp256 Montgomery images alike"""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 62) - 1)
+    return a
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the ark-ec VariableBaseMSM restatement on host cores, same config / metric / unit."""
+    if rank != 0:
+        return
+    from oracle import cref
+    n = 1 << LOG_N_PER_GPU
+    pts = cref.gen_points(0, SEED, n)
+    sc = rand_scalars(n, SEED + 1)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cref.msm_ark(0, pts, sc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cref.msm_ark(0, pts, sc)
+    dt = (time.perf_counter() - t0) / args.steps
+    mpts = n / dt / 1e6
+    cores = cref.num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": "Pallas MSM Mpts/s @2^20", "value": round(mpts, 4), "unit": "Mpts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": f"pallas_msm_2^{LOG_N_PER_GPU}_per_gpu", "points_per_gpu": n, "curve": "pallas",
+                   "note": "CPU restatement of ark-ec 0.2.0 VariableBaseMSM (c = ln-rule, rayon-over-windows -> OpenMP over windows); "
+                           "the Rust reference cannot be built in this image (no cargo)"},
+        "cpu_baseline": {"value": round(mpts, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
+                         "sample": f"one full 2^{LOG_N_PER_GPU}-point MSM per step, canonical scalars"},
+        "e2e": {"value": round(mpts, 4), "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=LOG_N_PER_GPU, help="log2 points per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import accumulation_b200 as ab
+    from accumulation_b200.sharded import ShardedMSM, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: accumulation_b200 has no CPU path")
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    ctx = ab.Context(local_rank)
+    n_per = 1 << args.log_n
+    n_total = n_per * world
+    start, count = shard_range(n_total, rank, world)
+
+    # ---- inputs: key shard generated on its own GPU; scalars seeded per rank, pinned on the host
+    key = ctx.register_synthetic_bases(ab.PALLAS, SEED, count, first_index=start)
+    sh = ShardedMSM(ctx, ab.PALLAS, key, n_total, rank, world, device=str(dev))
+    sc_np = rand_scalars(count, SEED + 1 + rank)
+    h_sc = torch.empty((count, 4), dtype=torch.int64).pin_memory()
+    h_sc.numpy().view(np.uint64)[:] = sc_np
+    d_sc = h_sc.to(dev)
+    d_stage = torch.empty_like(d_sc)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        return sh.msm_dev(d_sc, montgomery=False)
+
+    def step_e2e():
+        return sh.msm_host(h_sc, d_stage, montgomery=False)
+
+    # ---- warm-up (also sizes the workspace) and parity of the thing being timed
+    res = None
+    for _ in range(args.warmup):
+        res = step_dev()
+        step_e2e()
+    barrier()
+
+    # ---- timed region 1: device-resident scalars, per-step CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_acc = {}
+    barrier()
+    for a, b in evs:
+        flush.zero_()
+        a.record(stream)
+        step_dev()
+        b.record(stream)
+        if world == 1:
+            for k, v in ctx.last_timings().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+    barrier()
+    launches = ctx.kernel_launches() - launches0
+    t_dev_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    if world > 1:
+        for k, v in ctx.last_timings().items():
+            stage_acc[k] = v * args.steps
+
+    # ---- timed region 2: end to end from pinned host scalars (H2D inside), affine result read back on rank 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = step_e2e()
+    barrier()
+    t_e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    tt = torch.tensor([t_dev_ms, t_e2e_ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    t_dev_ms, t_e2e_ms = float(tt[0]), float(tt[1])
+    launches = int(lt[0])
+
+    # ---- ipa-pc-as decide tail (metric string: decide ms at degree 2^18, target 2^20), one GPU
+    decide = {}
+    if rank == 0 and world == 1:
+        for k in (18, 20):
+            if (1 << k) > count:
+                continue
+            ch = rand_scalars(k, SEED + 77)
+            fk = ctx.ipa_final_key(key, ch)
+            ts = []
+            for _ in range(5):
+                flush.zero_(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ok, _, _ = ctx.ipa_check_final_key(key, ch, fk[0], fk[1])
+                ts.append((time.perf_counter() - t0) * 1e3)
+                assert ok
+            decide[f"ipa_decide_tail_ms_2^{k}"] = round(statistics.median(ts), 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) and bit-exact check of the timed result against it
+    cpu = None
+    verified = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cref   # checker + reported baseline only
+        pts = ctx.download_bases(key)
+        t0 = time.perf_counter()
+        exp = cref.msm_ark(0, pts, sc_np)
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(count / dt / 1e6, 4), "unit": "Mpts/s", "cores": cref.num_threads(), "kind": "port",
+               "sample": f"one full 2^{args.log_n}-point MSM (same bases and scalars as the GPU step), {dt:.2f} s"}
+        if not args.no_verify:
+            verified = bool(res[1] == exp[1] and np.array_equal(res[0], exp[0]) and np.array_equal(res_e2e[0], exp[0]))
+            if not verified:
+                raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
+
+    hbm_peak, peak_kind = peaks()
+    value = n_total / (t_dev_ms * 1e-3) / 1e6
+    e2e = n_total / (t_e2e_ms * 1e-3) / 1e6
+    t_acc_ms = stage_acc.get("accumulate", 0.0) / args.steps
+    c = ctx_window_bits(count)
+    nwin = (256 + c - 1) // c
+    out = {
+        "metric": "Pallas MSM Mpts/s @2^20", "value": round(value, 3), "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(t_dev_ms, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": f"pallas_msm_2^{args.log_n}_per_gpu", "points_per_gpu": count, "points_total": n_total,
+                   "curve": "pallas", "scalars": "uniform 254-bit canonical (BigInteger256)", "window_bits": c, "windows": nwin,
+                   "sharding": f"point-range x{world}, all-gather of one 128 B partial per GPU" if world > 1 else "single GPU",
+                   "l2": "flushed (256 MiB memset) between timed steps", "timing": "CUDA events per step on the launching stream"},
+        "e2e": {"value": round(e2e, 3), "unit": "Mpts/s", "ms_per_step": round(t_e2e_ms, 4), "h2d_bytes_per_step": count * 32 * world,
+                "d2h_bytes_per_step": 65},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "stages_ms": {k: round(v / args.steps, 4) for k, v in stage_acc.items() if v},
+    }
+    if t_acc_ms > 0:
+        achieved = 96.0 * count / (t_acc_ms * 1e-3) / 1e9
+        out["roofline"] = {"kernel": "k_accumulate", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak,
+                           "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_kind": peak_kind,
+                           "algorithmic_bytes": 96 * count, "kernel_ms": round(t_acc_ms, 4)}
+        madds = count * nwin
+        gmul = madds * MULS_PER_MADD / (t_acc_ms * 1e-3) / 1e9
+        out["roofline_int"] = {"kernel": "k_accumulate", "bound": "imad (255-bit Montgomery products)", "achieved": round(gmul, 2),
+                               "peak": FE_MUL_PEAK_G, "unit": "Gmul/s", "frac": round(gmul / FE_MUL_PEAK_G, 4),
+                               "note": "bucket insertions x 10 field products (XYZZ mixed add) / kernel time; peak = measured "
+                                       "fe_mul microbenchmark (tools/ubench.cu), power-capped"}
+    if cpu:
+        out["cpu_baseline"] = cpu
+    if verified is not None:
+        out["verified_vs_oracle"] = verified
+    out.update(decide)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctx_window_bits(n):
+    """mirror of pick_window_bits() in accumulation_b200/csrc/accmsm.cu (reporting only)"""
+    lg = max(n, 1).bit_length() - 1
+    return min(16, max(4, lg - 3))
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,12 @@ const char *accmsm_stage_name(int stage);
 int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const uint8_t *infinity,
                           size_t n, uint64_t *handle);
 int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle);
+/* Seeded synthetic key generated on the device (benchmarks / tests): base i of the handle is
+ * s * G with G = (-1, 2) and s = the 254-bit SplitMix64 value of (seed, first_index + i), so a GPU can build
+ * its own shard of a larger key.  accmsm_download_bases copies registered bases back (x || y Montgomery). */
+int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, uint64_t first_index,
+                                    size_t n, uint64_t *handle);
+int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out);
 
 /* ---- MSM ------------------------------------------------------------------------------------------
  * ark_ec::msm::VariableBaseMSM::multi_scalar_mul(&bases[offset..offset+n], &scalars[..n]) followed by
@@ -78,6 +84,12 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
                   size_t hiding_index, const uint64_t *randomizer_mont, uint64_t out_xy[8],
                   uint8_t *out_inf);
 
+/* Scalars already resident in HBM (produced on the device by the vector kernels, or staged by the caller):
+ * d_scalars is a DEVICE pointer on ctx's GPU; the work is enqueued on `stream` (a cudaStream_t, NULL = the
+ * ctx stream) and the call blocks until the affine result is on the host. */
+int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
+                   int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf, void *stream);
+
 /* Device-resident variants for the multi-GPU path (one process per GPU): d_scalars is a
  * DEVICE pointer on ctx's GPU, the result is the un-normalised partial sum written to DEVICE memory
  * (16 x u64: X, Y, ZZ, ZZZ), `stream` is a cudaStream_t (NULL = the ctx stream; the call is then
@@ -85,9 +97,10 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
 int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n,
                            const void *d_scalars, int scalars_montgomery, void *d_out_partial,
                            void *stream);
-/* Sum k gathered partials (DEVICE, k x 16 u64) and normalise: the G-way add after the NCCL gather. */
+/* Sum k gathered partials (DEVICE, k x 16 u64) and normalise: the G-way add after the NCCL gather.
+ * Enqueued on `stream` (NULL = the ctx stream); blocks until the affine result is on the host. */
 int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k,
-                                uint64_t out_xy[8], uint8_t *out_inf);
+                                uint64_t out_xy[8], uint8_t *out_inf, void *stream);
 
 /* ---- IPA decider tail (K3 fused into K2) --------------------------------------------------------------
  * IpaPC::check_individual_opening_challenges after succinct_check (reached from

@@ -1,0 +1,286 @@
+"""GPU parity tests of the MSM / commitment path (K1 + K2 + K3 fused) through the C-ABI.
+
+Bit-exact against (i) the committed golden fixtures (independent Python big-int oracle), (ii) the C oracle
+restating ark-ec 0.2 VariableBaseMSM on the same seeded inputs, and (iii) at BASELINE.json's full size
+(2^20) size-independent properties: linearity, a checksum of partial MSMs, oracle agreement.
+Shapes follow the reference's own fixtures."""
+import numpy as np
+import pytest
+
+import accumulation_b200 as ab
+from oracle import cref, pyref
+from tests.util import (fe_canon, fe_mont, ints, load_golden, point_result, points_mont, same_point,
+                        scalar_distributions)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def keys(ctx):
+    """Per curve: 2^14 seeded bases registered once (like a trimmed commitment key)."""
+    out = {}
+    for curve in (0, 1):
+        pts = cref.gen_points(curve, 100 + curve, 1 << 14)
+        out[curve] = (pts, ctx.register_bases(curve, pts))
+    yield out
+    for _, b in out.values():
+        b.release()
+
+
+def test_msm_golden_vectors(ctx):
+    for case in load_golden("msm"):
+        curve = case["curve"]
+        bases = points_mont(curve, case["bases"])
+        exp = point_result(curve, case["result"])
+        B = ctx.register_bases(curve, bases)
+        try:
+            got = ctx.msm(B, fe_canon(ints(case["scalars"])), montgomery=False)
+            assert same_point(got, exp), case["name"]
+            got = ctx.msm(B, fe_mont(cref.scalar_field(curve), ints(case["scalars"])), montgomery=True)
+            assert same_point(got, exp), case["name"] + " (montgomery scalars)"
+        finally:
+            B.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 100, 1 << 10, 5000, 1 << 12, 1 << 14])
+def test_msm_sizes_vs_oracle(ctx, keys, curve, n):
+    pts, B = keys[curve]
+    sc = cref.gen_scalars(cref.scalar_field(curve), 7 * n + curve, n, montgomery=True)
+    assert same_point(ctx.msm(B, sc), cref.commit(curve, pts[:n], sc))
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_msm_canonical_scalars_and_offset(ctx, keys, curve):
+    pts, B = keys[curve]
+    sf = cref.scalar_field(curve)
+    sc = cref.gen_scalars(sf, 5, 3000, montgomery=False)
+    assert same_point(ctx.msm(B, sc, montgomery=False), cref.msm_ark(curve, pts[:3000], sc))
+    scm = cref.gen_scalars(sf, 77, 1000, True)
+    assert same_point(ctx.msm(B, scm, offset=123), cref.commit(curve, pts[123:1123], scm))
+    # n = 0 is the identity (0, 1, infinity) like ark-ec
+    xy, inf = ctx.msm(B, np.zeros((0, 4), np.uint64))
+    assert inf == 1 and same_point((xy, inf), point_result(curve, None))
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("n", [33, 4096])
+def test_msm_reference_fixture_distributions(ctx, keys, curve, n):
+    """constant vectors, (a,..,a,0), zero / one / q-1, one-hot, 128-bit challenges: one hot bucket per window."""
+    pts, B = keys[curve]
+    for name, sc in scalar_distributions(curve, n, 900 + n).items():
+        assert same_point(ctx.msm(B, sc), cref.commit(curve, pts[:n], sc)), name
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_msm_duplicate_and_opposite_bases(ctx, curve):
+    """examples/scaling-as.rs:91-92 duplicates accumulators: P + P and P + (-P) inside one bucket."""
+    sf = cref.scalar_field(curve)
+    base = cref.gen_points(curve, 3, 64)
+    bm = pyref.base_modulus(curve)
+    neg = base.copy()
+    y = cref.from_mont(cref.base_field(curve), base[:, 4:])
+    neg[:, 4:] = cref.to_mont(cref.base_field(curve), cref.ints_to_arr([(bm - v) % bm for v in cref.arr_to_ints(y)]))
+    pts = np.concatenate([base, base, neg, base[:1].repeat(200, axis=0)])
+    one = cref.gen_scalars(sf, 4, 1, True)
+    rnd = cref.gen_scalars(sf, 5, pts.shape[0], True)
+    B = ctx.register_bases(curve, pts)
+    try:
+        for sc in (np.repeat(one, pts.shape[0], axis=0), rnd):
+            assert same_point(ctx.msm(B, sc), cref.commit(curve, pts, sc))
+    finally:
+        B.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_identity_bases_contribute_nothing(ctx, curve):
+    sf = cref.scalar_field(curve)
+    pts = cref.gen_points(curve, 8, 300)
+    inf = (np.arange(300) % 7 == 0).astype(np.uint8)
+    sc = cref.gen_scalars(sf, 9, 300, False)
+    B = ctx.register_bases(curve, pts, inf)
+    try:
+        assert same_point(ctx.msm(B, sc, montgomery=False), cref.msm_ark(curve, pts, sc, bases_inf=inf))
+    finally:
+        B.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_commit_with_randomizer(ctx, keys, curve):
+    """PedersenCommitment::commit(ck, elems, Some(r)) = MSM + r * hiding_generator (App. A.2)."""
+    pts, B = keys[curve]
+    sf = cref.scalar_field(curve)
+    for n in (0, 1, 777):
+        el = cref.gen_scalars(sf, 21 + n, n, True)
+        r = cref.gen_scalars(sf, 22 + n, 1, True).reshape(4)
+        got = ctx.commit(B, el, hiding_index=1000, randomizer_mont=r)
+        assert same_point(got, cref.commit(curve, pts[:n], el, pts[1000], r))
+    ck = ab.CommitterKey.new(ctx, curve, pts[:500], pts[500])
+    el = cref.gen_scalars(sf, 30, 500, True)
+    r = cref.gen_scalars(sf, 31, 1, True).reshape(4)
+    assert same_point(ab.PedersenCommitment.commit(ck, el, r), cref.commit(curve, pts[:500], el, pts[500], r))
+    assert same_point(ab.PedersenCommitment.commit(ck, el), cref.commit(curve, pts[:500], el))
+    # elems longer than the key are truncated like ark-ec's zip
+    el2 = cref.gen_scalars(sf, 32, 600, True)
+    assert same_point(ab.PedersenCommitment.commit(ck, el2), cref.commit(curve, pts[:500], el2[:500]))
+    ck.bases.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_msm_batch(ctx, keys, curve):
+    pts, B = keys[curve]
+    sf = cref.scalar_field(curve)
+    n, k = 2048, 3
+    sc = cref.gen_scalars(sf, 40, n * k, True).reshape(k, n, 4)
+    xy, inf = ctx.msm_batch(B, sc)
+    for j in range(k):
+        assert same_point((xy[j], inf[j]), cref.commit(curve, pts[:n], sc[j]))
+
+
+@pytest.mark.parametrize("c", [4, 7, 8, 11, 13, 15, 16])
+def test_window_bits_sweep(ctx, keys, c):
+    """every signed-digit window width gives the same point (the final-carry bug lives here, App. D.4)."""
+    pts, B = keys[0]
+    q = pyref.scalar_modulus(0)
+    n = 600
+    vals = [q - 1, q - 2, (1 << 254), (1 << 254) - 1, (1 << 255) % q, 1, 0] + [pyref.SplitMix64(c).field(q) for _ in range(n - 7)]
+    sc = cref.ints_to_arr(vals)
+    ctx.set_window_bits(c)
+    try:
+        assert same_point(ctx.msm(B, sc, montgomery=False), cref.msm_ark(0, pts[:n], sc))
+    finally:
+        ctx.set_window_bits(0)
+
+
+def test_ipa_golden_vectors(ctx):
+    for case in load_golden("ipa"):
+        curve = case["curve"]
+        sf = cref.scalar_field(curve)
+        ch = fe_mont(sf, ints(case["challenges"]))
+        key = points_mont(curve, case["key"])
+        exp = point_result(curve, case["final_key"])
+        B = ctx.register_bases(curve, key)
+        try:
+            assert same_point(ctx.ipa_final_key(B, ch), exp)
+            ok, xy, inf = ctx.ipa_check_final_key(B, ch, exp[0], exp[1])
+            assert ok and same_point((xy, inf), exp)
+            bad = exp[0].copy(); bad[5] ^= np.uint64(1 << 17)
+            assert not ctx.ipa_check_final_key(B, ch, bad, 0)[0]
+            assert (ctx.compute_coeffs(sf, ch) == fe_mont(sf, ints(case["coeffs"]))).all()
+        finally:
+            B.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("k", [0, 1, 4, 10, 14])
+def test_ipa_decide_tail_vs_oracle(ctx, keys, curve, k):
+    """decide = check: final_key = cm_commit(key, h.compute_coeffs()) == proof.final_comm_key
+    (src/ipa_pc_as/mod.rs:836-845); reject on any corrupted challenge / key / expected point."""
+    pts, B = keys[curve]
+    sf = cref.scalar_field(curve)
+    ch = cref.gen_scalars(sf, 1000 + k, k, True)
+    got = ctx.ipa_final_key(B, ch)
+    ok, exp_xy, exp_inf = cref.ipa_check_final_key(curve, pts[: 1 << k], ch, got[0], got[1])
+    assert ok and same_point(got, (exp_xy, exp_inf))
+    if k <= 10:   # two independent computations of the same point: MSM(key, coeffs) == key folded k times
+        assert same_point(got, cref.ipa_fold_key(curve, pts[: 1 << k], ch))
+    assert ab.InnerProductArgPC.check_final_key(ab.CommitterKey(B, B.n), ch, exp_xy, exp_inf)
+    if k:
+        bad = ch.copy(); bad[k // 2, 1] ^= np.uint64(4)
+        assert not ctx.ipa_check_final_key(B, bad, exp_xy, exp_inf)[0]
+
+
+def test_msm_full_size_2_20(ctx):
+    """BASELINE config 5 headline size: oracle agreement, linearity and the split-sum checksum at 2^20."""
+    n = 1 << 20
+    pts = cref.gen_points(0, 0xACC5, n)
+    B = ctx.register_bases(0, pts)
+    try:
+        a = cref.gen_scalars(cref.FQ, 1, n, True)
+        b = cref.gen_scalars(cref.FQ, 2, n, True)
+        ca, cb = ctx.msm(B, a), ctx.msm(B, b)
+        assert same_point(ca, cref.commit(0, pts, a))
+        cab = ctx.msm(B, cref.fe_add(cref.FQ, a, b))
+        assert same_point(cref.point_add(0, ca[0], ca[1], cb[0], cb[1]), cab)          # linearity
+        h = n // 2 + 12345                                                             # checksum of partial sums
+        lo, hi = ctx.msm(B, a[:h]), ctx.msm(B, a[h:], offset=h)
+        assert same_point(cref.point_add(0, lo[0], lo[1], hi[0], hi[1]), ca)
+        const = np.repeat(a[:1], n, axis=0)                                            # hot bucket at full size
+        assert same_point(ctx.msm(B, const), cref.commit(0, pts, const))
+        # ipa decide tail at degree 2^20 (config 4, one GPU)
+        ch = cref.gen_scalars(cref.FQ, 3, 20, True)
+        got = ctx.ipa_final_key(B, ch)
+        assert same_point(got, cref.commit(0, pts, cref.compute_coeffs(cref.FQ, ch)))
+    finally:
+        B.release()
+
+
+def _splitmix64(x):
+    m = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & m
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & m
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & m
+    return x ^ (x >> 31)
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_synthetic_bases(ctx, curve):
+    """register_synthetic_bases: base i = s_i * G, reproducible per global index (shards line up)."""
+    seed, n = 0xACC5, 300
+    B = ctx.register_synthetic_bases(curve, seed, n)
+    pts = ctx.download_bases(B)
+    bf = cref.base_field(curve)
+    G = fe_mont(bf, list(pyref.generator(curve))).reshape(8)
+    for i in (0, 1, 17, n - 1):
+        assert cref.on_curve(curve, pts[i])
+        words = [_splitmix64(seed ^ _splitmix64(i * 4 + j)) for j in range(4)]
+        s = sum(w << (64 * j) for j, w in enumerate(words))
+        s = (s & ((1 << 254) - 1)) | 1
+        exp, inf = cref.point_mul(curve, G, 0, cref.from_int(s))
+        assert inf == 0 and np.array_equal(exp, pts[i])
+    B2 = ctx.register_synthetic_bases(curve, seed, 100, first_index=150)
+    assert np.array_equal(ctx.download_bases(B2), pts[150:250])
+    sc = cref.gen_scalars(cref.scalar_field(curve), 5, n, True)
+    assert same_point(ctx.msm(B, sc), cref.commit(curve, pts, sc))
+    B.release(); B2.release()
+
+
+def test_device_resident_scalars_and_sharded_flow(ctx, keys):
+    """accmsm_msm_dev and the partial/combine pair used by the one-process-per-GPU sharding (8e), driven from
+    one process: 3 point-range shards -> 3 partials -> combine == whole MSM; same for the IPA decider tail."""
+    import torch
+    from accumulation_b200.sharded import ShardedMSM, shard_range
+    pts, B = keys[0]
+    n = 1 << 13
+    sc = cref.gen_scalars(cref.FQ, 300, n, True)
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    exp = cref.commit(0, pts[:n], sc)
+    st = torch.cuda.current_stream().cuda_stream
+    assert same_point(ctx.msm_dev(B, d_sc.data_ptr(), n, stream=st), exp)
+    assert same_point(ctx.msm_dev(B, d_sc.data_ptr(), n), exp)
+    world = 3
+    parts = torch.zeros((world, 16), dtype=torch.int64, device="cuda")
+    for r in range(world):
+        lo, cnt = shard_range(n, r, world)
+        ctx.msm_partial_dev(B, d_sc[lo:].data_ptr(), cnt, parts[r].data_ptr(), offset=lo, stream=st)
+    assert same_point(ctx.combine_partials_dev(0, parts.data_ptr(), world, stream=st), exp)
+    # IPA: coefficient ranges expanded per shard
+    k = 13
+    ch = cref.gen_scalars(cref.FQ, 301, k, True)
+    whole = ctx.ipa_final_key(B, ch)
+    shards = []
+    for r in range(world):
+        lo, cnt = shard_range(n, r, world)
+        Br = ctx.register_bases(0, pts[lo:lo + cnt])
+        shards.append(Br)
+        ctx.ipa_final_key_partial_dev(Br, ch, lo, cnt, parts[r].data_ptr(), stream=st)
+    assert same_point(ctx.combine_partials_dev(0, parts.data_ptr(), world, stream=st), whole)
+    for Br in shards:
+        Br.release()
+    # world = 1 ShardedMSM wrapper (what bench.py drives)
+    sh = ShardedMSM(ctx, 0, pts[:n], n, 0, 1)
+    assert same_point(sh.msm_dev(d_sc), exp)
+    h_sc = torch.from_numpy(sc.view(np.int64)).pin_memory()
+    assert same_point(sh.msm_host(h_sc, torch.empty_like(d_sc)), exp)
+    assert same_point(sh.ipa_final_key(ch, k), whole)
+    sh.release()
