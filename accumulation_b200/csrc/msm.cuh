@@ -221,6 +221,14 @@ ACC_D void seg_scan(xyzz_t *pt, const uint32_t *id, uint32_t ns) {
     // yet (writes of a phase land in its own stripe, reads come from it or from lower stripes) and one
     // point per thread is live at a time.
     for (uint32_t d = 1; d < ns; d <<= 1) {
+        // equal ids are contiguous: if no slot has a partner at distance d, none has one further away
+        bool any = false;
+#pragma unroll 1
+        for (int r = 0; r < PER_T; r++) {
+            uint32_t i = threadIdx.x + r * blockDim.x;
+            any |= i < ns && i >= d && id[i] != NONE_ID && id[i] == id[i - d];
+        }
+        if (!__syncthreads_or(any)) break;
 #pragma unroll 1
         for (int r = PER_T - 1; r >= 0; r--) {
             uint32_t i = threadIdx.x + r * blockDim.x;
@@ -255,8 +263,12 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
     const uint32_t s = s64 < M ? (uint32_t)s64 : M;
     const uint32_t e = (s64 + L < M) ? (uint32_t)(s64 + L) : M;
 
-    xyzz_t head = Cv::identity(), tail = Cv::identity();
+    // slot 2t = the first run of the slice (may continue the previous thread's last run), slot 2t + 1 = the
+    // last run (may continue into the next thread's slice); written straight to shared memory so that only
+    // one accumulator lives in registers
     uint32_t head_id = NONE_ID, tail_id = NONE_ID;
+    slot_pt[2 * threadIdx.x + 1] = Cv::identity();
+    if (s >= e) slot_pt[2 * threadIdx.x] = Cv::identity();
 
     if (s < e) {
         // bucket containing entry s: first k with offsets[k + 1] > s
@@ -265,29 +277,35 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
             uint32_t mid = (lo + hi) >> 1;
             if (offsets[mid + 1] > s) hi = mid; else lo = mid + 1;
         }
-        uint32_t k = lo, pos = s, nruns = 0;
-        while (pos < e) {
-            const uint32_t bend = offsets[k + 1];
-            const uint32_t rend = bend < e ? bend : e;
-            xyzz_t acc = Cv::identity();
-            for (uint32_t p = pos; p < rend; p++) {
-                uint32_t ent = entries[p];
-                affine_t pt = load_affine(bases + (ent & 0x7fffffffu));
-                if (ent >> 31) pt.y = Cv::F::neg(pt.y);
-                Cv::madd(acc, pt);
+        // One flat loop over the slice: every lane of a warp executes exactly L iterations and spends them
+        // in the mixed add; a bucket boundary only costs the (cheap, divergent) flush of the finished run.
+        uint32_t k = lo, bend = offsets[k + 1];
+        bool first_run = true;
+        xyzz_t acc = Cv::identity();
+        uint32_t ent = entries[s];
+        affine_t pt = load_affine(bases + (ent & 0x7fffffffu));
+#pragma unroll 1
+        for (uint32_t p = s; p < e; p++) {
+            if (p == bend) {                       // the run of bucket k ended with entry p - 1
+                if (first_run) { slot_pt[2 * threadIdx.x] = acc; head_id = k; first_run = false; }
+                else store_xyzz(buckets + k, acc);  // a run strictly inside this slice is complete
+                acc = Cv::identity();
+                do { k++; bend = offsets[k + 1]; } while (bend == p);
             }
-            pos = rend;
-            if (nruns == 0) { head = acc; head_id = k; }
-            else if (pos < e) store_xyzz(buckets + k, acc);     // a run strictly inside this slice is complete
-            else { tail = acc; tail_id = k; }
-            nruns++;
-            if (pos < e) { do { k++; } while (offsets[k + 1] == pos); }
+            const uint32_t cur_sign = ent >> 31;
+            affine_t cur = pt;
+            if (p + 1 < e) {                       // software prefetch of the next point (a gather from HBM / L2)
+                ent = entries[p + 1];
+                pt = load_affine(bases + (ent & 0x7fffffffu));
+            }
+            if (cur_sign) cur.y = Cv::F::neg(cur.y);
+            Cv::madd(acc, cur);
         }
-        if (tail_id == NONE_ID) tail_id = head_id;   // keep equal ids contiguous for the segmented scan
+        if (first_run) { slot_pt[2 * threadIdx.x] = acc; head_id = k; tail_id = k; }   // equal ids stay contiguous
+        else { slot_pt[2 * threadIdx.x + 1] = acc; tail_id = k; }
     }
-
-    slot_pt[2 * threadIdx.x] = head; slot_id[2 * threadIdx.x] = head_id;
-    slot_pt[2 * threadIdx.x + 1] = tail; slot_id[2 * threadIdx.x + 1] = tail_id;
+    slot_id[2 * threadIdx.x] = head_id;
+    slot_id[2 * threadIdx.x + 1] = tail_id;
     __syncthreads();
     const uint32_t ns = 2 * ACC_THREADS;
     seg_scan<CURVE, 2>(slot_pt, slot_id, ns);
