@@ -276,6 +276,12 @@ class Bases:
     handle: int
     n: int
 
+    def precompute(self, window_bits: int = 0) -> "Bases":
+        """build the window table (accmsm_precompute_bases); later MSMs on this key use a single bucket set"""
+        self.ctx._check(self.ctx._lib.accmsm_precompute_bases(self.ctx._h, C.c_uint64(self.handle), C.c_int(window_bits)),
+                        "precompute_bases")
+        return self
+
     def release(self):
         if self.handle:
             self.ctx._check(self.ctx._lib.accmsm_release_bases(self.ctx._h, C.c_uint64(self.handle)), "release_bases")

@@ -25,6 +25,9 @@ struct Bases {
     size_t n = 0;
     affine_t *d_xy = nullptr;
     uint8_t *d_inf = nullptr;   // nullptr when no base is the identity
+    // optional window table (accmsm_precompute_bases): d_table[w * n + i] = 2^(pre_c * w) * base_i
+    affine_t *d_table = nullptr;
+    uint32_t pre_c = 0, pre_nwin = 0;
 };
 
 template <class T> struct DevBuf {
@@ -114,13 +117,34 @@ uint32_t pick_window_bits(const accmsm_ctx *ctx, size_t n) {
     return (uint32_t)std::min(16, std::max(4, c));
 }
 
-MsmShape make_shape(const accmsm_ctx *ctx, size_t n) {
+// The window table is used when the MSM is large enough for the table's (fixed) bucket count to pay off
+// and no explicit window override asks for something else.
+bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
+    if (!B.d_table) return false;
+    if (ctx->window_bits && (uint32_t)ctx->window_bits != B.pre_c) return false;
+    return n >= (size_t(1) << (B.pre_c > 4 ? B.pre_c - 4 : 0));
+}
+
+MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n) {
     MsmShape sh;
     sh.n = (uint32_t)n;
-    sh.c = pick_window_bits(ctx, n);
-    sh.nwin = (256 + sh.c - 1) / sh.c;
-    sh.nb = 1u << (sh.c - 1);
-    sh.nkeys = sh.nwin * sh.nb;
+    if (use_table(ctx, B, n)) {
+        sh.c = B.pre_c;
+        sh.nwin = B.pre_nwin;
+        sh.nb = 1u << (sh.c - 1);
+        sh.nkeys = sh.nb;
+        sh.hist_stride = 0;
+        sh.ent_stride = (uint32_t)B.n;
+        sh.ent_offset = (uint32_t)offset;
+    } else {
+        sh.c = pick_window_bits(ctx, n);
+        sh.nwin = (256 + sh.c - 1) / sh.c;
+        sh.nb = 1u << (sh.c - 1);
+        sh.nkeys = sh.nwin * sh.nb;
+        sh.hist_stride = sh.nb;
+        sh.ent_stride = 0;
+        sh.ent_offset = 0;
+    }
     return sh;
 }
 
@@ -129,7 +153,10 @@ MsmShape make_shape(const accmsm_ctx *ctx, size_t n) {
 template <int CURVE, class Src>
 int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src &src, const uint8_t *d_inf,
             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st) {
-    MsmShape sh = make_shape(ctx, n);
+    MsmShape sh = make_shape(ctx, B, offset, n);
+    const bool tabled = sh.ent_stride != 0;
+    const uint32_t nsets = tabled ? 1u : sh.nwin;              // bucket sets to reduce and combine
+    const affine_t *points = tabled ? B.d_table : B.d_xy + offset;
     const size_t n_entries = (size_t)sh.n * sh.nwin;
     CU(ctx, ctx->digits.ensure(n_entries));
     CU(ctx, ctx->entries.ensure(n_entries));
@@ -166,7 +193,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
         CU(ctx, ctx->cta_parts.ensure(2 * grid));
         size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
         k_accumulate<CURVE><<<grid, ACC_THREADS, smem, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p,
-                                                              B.d_xy + offset, ctx->buckets.p,
+                                                              points, ctx->buckets.p,
                                                               ctx->cta_ids.p, ctx->cta_parts.p);
         mark(ctx, ST_FIXUP, st);
         uint32_t ns = 2 * grid;
@@ -179,11 +206,11 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
     {
         uint32_t seg = std::min<uint32_t>(RED0_SEG, sh.nb);
         uint32_t per_set = sh.nb / seg;
-        uint32_t items = per_set * sh.nwin;
+        uint32_t items = per_set * nsets;
         CU(ctx, ctx->red_sum[0].ensure(items));
         CU(ctx, ctx->red_wsum[0].ensure(items));
-        CU(ctx, ctx->red_sum[1].ensure(items / 32 + sh.nwin));
-        CU(ctx, ctx->red_wsum[1].ensure(items / 32 + sh.nwin));
+        CU(ctx, ctx->red_sum[1].ensure(items / 32 + nsets));
+        CU(ctx, ctx->red_wsum[1].ensure(items / 32 + nsets));
         k_reduce0<CURVE><<<(items + 127) / 128, 128, 0, st>>>(ctx->offsets.p, ctx->buckets.p, sh.nb, seg, items,
                                                               ctx->red_sum[0].p, ctx->red_wsum[0].p);
         ctx->launches++;
@@ -192,9 +219,9 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
         int cur = 0;
         while (per_set > 1) {
             uint32_t per_out = (per_set + 31) / 32;
-            uint32_t warps = per_out * sh.nwin;
+            uint32_t warps = per_out * nsets;
             k_reduce1<CURVE><<<(warps * 32 + 127) / 128, 128, 0, st>>>(ctx->red_sum[cur].p, ctx->red_wsum[cur].p, per_set,
-                                                                       per_out, sh.nwin, log2_span,
+                                                                       per_out, nsets, log2_span,
                                                                        ctx->red_sum[cur ^ 1].p, ctx->red_wsum[cur ^ 1].p);
             ctx->launches++;
             log2_span += 5;
@@ -204,7 +231,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
         window_sums = ctx->red_wsum[cur].p;
     }
     mark(ctx, ST_FINISH, st);
-    k_finish<CURVE><<<1, 32, 0, st>>>(window_sums, sh.nwin, sh.c, d_extra, n_extra, normalise ? 1 : 0, d_partial,
+    k_finish<CURVE><<<1, 32, 0, st>>>(window_sums, nsets, sh.c, d_extra, n_extra, normalise ? 1 : 0, d_partial,
                                       ctx->d_out_affine, ctx->d_out_inf);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
@@ -329,7 +356,11 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (auto &kv : ctx->bases) { cudaFree(kv.second.d_xy); if (kv.second.d_inf) cudaFree(kv.second.d_inf); }
+    for (auto &kv : ctx->bases) {
+        cudaFree(kv.second.d_xy);
+        if (kv.second.d_inf) cudaFree(kv.second.d_inf);
+        if (kv.second.d_table) cudaFree(kv.second.d_table);
+    }
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release();
@@ -404,6 +435,32 @@ int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, u
     return ACCMSM_OK;
 }
 
+int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
+    if (!ctx || window_bits < 0 || (window_bits && (window_bits < 8 || window_bits > 16)))
+        return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 8..16");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->bases.find(handle);
+    if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }
+    Bases &B = it->second;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (B.d_table) { cudaFree(B.d_table); B.d_table = nullptr; B.pre_c = B.pre_nwin = 0; }
+    if (B.n == 0) return ACCMSM_OK;
+    uint32_t c = window_bits ? (uint32_t)window_bits : 16u;
+    uint32_t nwin = (256 + c - 1) / c;
+    if ((size_t)nwin * B.n >= (size_t(1) << 31)) return fail_arg(ctx, "precompute_bases: windows * n must be < 2^31");
+    affine_t *table = nullptr;
+    CU(ctx, cudaMalloc(&table, (size_t)nwin * B.n * sizeof(affine_t)));
+    uint32_t blocks = (uint32_t)((B.n + 127) / 128);
+    if (B.curve == 0) k_precompute<0><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+    else k_precompute<1><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+    ctx->launches++;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(table); CU(ctx, e); }
+    B.d_table = table; B.pre_c = c; B.pre_nwin = nwin;
+    return ACCMSM_OK;
+}
+
 int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out) {
     if (!ctx || (n && !xy_out)) return fail_arg(ctx, "download_bases: bad argument");
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -425,6 +482,7 @@ int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(it->second.d_xy);
     if (it->second.d_inf) cudaFree(it->second.d_inf);
+    if (it->second.d_table) cudaFree(it->second.d_table);
     ctx->bases.erase(it);
     return ACCMSM_OK;
 }

@@ -33,7 +33,13 @@ struct MsmShape {
     uint32_t c;        // window bits
     uint32_t nwin;     // number of signed windows = ceil(256 / c)
     uint32_t nb;       // buckets per window = 2^(c-1)
-    uint32_t nkeys;    // nwin * nb
+    uint32_t nkeys;    // bucket sets * nb
+    // Two sort layouts.  Plain key: every window has its own bucket set (hist_stride = nb) and an entry is the
+    // point index.  Precomputed key (table[w][i] = 2^(c w) P_i): all windows share ONE bucket set
+    // (hist_stride = 0) and an entry indexes the table: w * ent_stride + ent_offset + i.
+    uint32_t hist_stride;
+    uint32_t ent_stride;
+    uint32_t ent_offset;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
         }
         digits[(size_t)w * sh.n + i] = enc;
         uint32_t mag = enc & 0x7fffffffu;
-        if (mag) atomicAdd(&hist[w * sh.nb + mag - 1], 1u);
+        if (mag) atomicAdd(&hist[w * sh.hist_stride + mag - 1], 1u);
     }
 }
 
@@ -203,8 +209,8 @@ __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__
         uint32_t enc = digits[(size_t)w * sh.n + i];
         uint32_t mag = enc & 0x7fffffffu;
         if (mag) {
-            uint32_t pos = atomicAdd(&cursor[w * sh.nb + mag - 1], 1u);
-            entries[pos] = i | (enc & 0x80000000u);
+            uint32_t pos = atomicAdd(&cursor[w * sh.hist_stride + mag - 1], 1u);
+            entries[pos] = (w * sh.ent_stride + sh.ent_offset + i) | (enc & 0x80000000u);
         }
     }
 }
@@ -456,6 +462,47 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
         Cv::to_affine(acc, a, inf);
         store_fe(&out_affine->x, a.x); store_fe(&out_affine->y, a.y);
         *out_inf = inf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_precompute: table[w * n + i] = 2^(c w) * P_i in affine form, w < nwin.  One thread per base walks the
+// doubling chain in XYZZ, keeps the nwin - 1 intermediate points in local memory and normalises them with
+// ONE inversion (Montgomery batch inversion over its own chain).  Run once per registered key: commitment
+// keys are fixed for the life of a prover (trim / index time), so the MSM then needs a single bucket set,
+// one bucket reduction and no window doublings.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_PRE_WINDOWS = 32;
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_precompute(const affine_t *__restrict__ bases, uint32_t n, uint32_t c,
+                                                     uint32_t nwin, affine_t *__restrict__ table) {
+    using Cv = Curve<CURVE>;
+    using F = typename Cv::F;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p = load_affine(bases + i);
+    store_fe(&table[i].x, p.x); store_fe(&table[i].y, p.y);
+    xyzz_t pts[MAX_PRE_WINDOWS];
+    fe_t pref[MAX_PRE_WINDOWS];
+    xyzz_t cur = Cv::from_affine(p);
+    fe_t run = F::one();
+#pragma unroll 1
+    for (uint32_t w = 1; w < nwin; w++) {
+#pragma unroll 1
+        for (uint32_t b = 0; b < c; b++) cur = Cv::dbl(cur);
+        pts[w] = cur;
+        pref[w] = run;
+        run = F::mul(run, cur.zzz);
+    }
+    fe_t inv = F::inv(run);
+#pragma unroll 1
+    for (uint32_t w = nwin - 1; w >= 1; w--) {
+        fe_t t = F::mul(inv, pref[w]);            // ZZZ_w^-1
+        inv = F::mul(inv, pts[w].zzz);
+        fe_t zt = F::mul(pts[w].zz, t);           // ZZ^-1 = (ZZ t)^2 since ZZ^3 = ZZZ^2
+        affine_t *dst = table + (size_t)w * n + i;
+        store_fe(&dst->x, F::mul(pts[w].x, F::sqr(zt)));
+        store_fe(&dst->y, F::mul(pts[w].y, t));
     }
 }
 

@@ -58,6 +58,11 @@ const char *accmsm_stage_name(int stage);
 int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const uint8_t *infinity,
                           size_t n, uint64_t *handle);
 int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle);
+/* Optional, once per key: build the window table 2^(c w) * base_i (w < ceil(256/c), c = window_bits, 0 = 16)
+ * next to the key (ceil(256/c) x 64 B per base).  Commitment keys are fixed from trim / index time on
+ * (src/ipa_pc_as/mod.rs:507-513, src/hp_as/mod.rs:640-641), so every later MSM on the handle then uses ONE
+ * bucket set: one bucket reduction and no window doublings.  Results are identical with or without it. */
+int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits);
 /* Seeded synthetic key generated on the device (benchmarks / tests): base i of the handle is
  * s * G with G = (-1, 2) and s = the 254-bit SplitMix64 value of (seed, first_index + i), so a GPU can build
  * its own shard of a larger key.  accmsm_download_bases copies registered bases back (x || y Montgomery). */

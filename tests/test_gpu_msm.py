@@ -190,11 +190,14 @@ def test_ipa_decide_tail_vs_oracle(ctx, keys, curve, k):
         assert not ctx.ipa_check_final_key(B, bad, exp_xy, exp_inf)[0]
 
 
-def test_msm_full_size_2_20(ctx):
+@pytest.mark.parametrize("precompute", [False, True])
+def test_msm_full_size_2_20(ctx, precompute):
     """BASELINE config 5 headline size: oracle agreement, linearity and the split-sum checksum at 2^20."""
     n = 1 << 20
     pts = cref.gen_points(0, 0xACC5, n)
     B = ctx.register_bases(0, pts)
+    if precompute:
+        B.precompute()
     try:
         a = cref.gen_scalars(cref.FQ, 1, n, True)
         b = cref.gen_scalars(cref.FQ, 2, n, True)
@@ -284,3 +287,32 @@ def test_device_resident_scalars_and_sharded_flow(ctx, keys):
     assert same_point(sh.msm_host(h_sc, torch.empty_like(d_sc)), exp)
     assert same_point(sh.ipa_final_key(ch, k), whole)
     sh.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("c", [0, 8, 11, 13])
+def test_precomputed_window_table(ctx, curve, c):
+    """accmsm_precompute_bases: table[w][i] = 2^(c w) P_i, one shared bucket set.  Same points bit for bit
+    as the plain path and the oracle, for every size / distribution / offset / commit / IPA entry point."""
+    sf = cref.scalar_field(curve)
+    N = 1 << 13
+    pts = cref.gen_points(curve, 500 + curve, N)
+    B = ctx.register_bases(curve, pts).precompute(c)
+    try:
+        for n in (1, 33, 1000, 4096, 5000, N):          # small n falls back to per-window buckets
+            sc = cref.gen_scalars(sf, 600 + n, n, True)
+            assert same_point(ctx.msm(B, sc), cref.commit(curve, pts[:n], sc)), n
+        n = 4500
+        for name, sc in scalar_distributions(curve, n, 700).items():
+            assert same_point(ctx.msm(B, sc), cref.commit(curve, pts[:n], sc)), name
+        sc = cref.gen_scalars(sf, 701, 4200, False)
+        assert same_point(ctx.msm(B, sc, montgomery=False, offset=777), cref.msm_ark(curve, pts[777:777 + 4200], sc))
+        el = cref.gen_scalars(sf, 702, 6000, True)
+        r = cref.gen_scalars(sf, 703, 1, True).reshape(4)
+        assert same_point(ctx.commit(B, el, hiding_index=N - 1, randomizer_mont=r), cref.commit(curve, pts[:6000], el, pts[N - 1], r))
+        ch = cref.gen_scalars(sf, 704, 13, True)
+        got = ctx.ipa_final_key(B, ch)
+        assert same_point(got, cref.commit(curve, pts, cref.compute_coeffs(sf, ch)))
+        assert ctx.ipa_check_final_key(B, ch, got[0], got[1])[0]
+    finally:
+        B.release()
