@@ -60,7 +60,7 @@ struct accmsm_ctx {
     int acc_ctas_per_sm[2] = {0, 0};
 
     // MSM workspace
-    DevBuf<uint32_t> digits, hist, offsets, cursor, entries, cta_ids;
+    DevBuf<uint32_t> digits, hist, offsets, cursor, entries, cta_ids, tile_sums, tile_offs;
     DevBuf<xyzz_t> buckets, red_sum[2], red_wsum[2], cta_parts, partial;
     DevBuf<uint8_t> scalars, misc;
     affine_t *d_out_affine = nullptr;
@@ -173,8 +173,20 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
         ctx->launches++;
     }
     mark(ctx, ST_SCAN, st);
-    k_scan<<<1, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p);
-    ctx->launches++;
+    {
+        uint32_t ntiles = (sh.nkeys + SCAN_TILE - 1) / SCAN_TILE;
+        if (ntiles <= SCAN_ONE_CTA_TILES) {
+            k_scan<<<1, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p);
+            ctx->launches++;
+        } else {
+            CU(ctx, ctx->tile_sums.ensure(ntiles));
+            CU(ctx, ctx->tile_offs.ensure(ntiles + 1));
+            k_scan_tile_sums<<<ntiles, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->tile_sums.p);
+            k_scan<<<1, 1024, 0, st>>>(ctx->tile_sums.p, ntiles, ctx->tile_offs.p, nullptr);
+            k_scan_tiles<<<ntiles, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->tile_offs.p, ctx->offsets.p, ctx->cursor.p);
+            ctx->launches += 3;
+        }
+    }
     mark(ctx, ST_SCATTER, st);
     {
         uint32_t blocks = (sh.n + 255) / 256;
@@ -362,7 +374,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
         if (kv.second.d_table) cudaFree(kv.second.d_table);
     }
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
-    ctx->cta_ids.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
+    ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release();
     for (int i = 0; i < 2; i++) { ctx->red_sum[i].release(); ctx->red_wsum[i].release(); }
     if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
@@ -436,8 +448,8 @@ int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, u
 }
 
 int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
-    if (!ctx || window_bits < 0 || (window_bits && (window_bits < 8 || window_bits > 16)))
-        return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 8..16");
+    if (!ctx || window_bits < 0 || (window_bits && (window_bits < 8 || window_bits > 22)))
+        return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 8..22");
     std::lock_guard<std::mutex> lock(ctx->mu);
     auto it = ctx->bases.find(handle);
     if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }
@@ -446,7 +458,11 @@ int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (B.d_table) { cudaFree(B.d_table); B.d_table = nullptr; B.pre_c = B.pre_nwin = 0; }
     if (B.n == 0) return ACCMSM_OK;
-    uint32_t c = window_bits ? (uint32_t)window_bits : 16u;
+    // auto: about one bucket per two points, measured best at 2^20 (profiles/r01b_window_sweep.txt): fewer
+    // windows mean fewer bucket insertions, and the single bucket set keeps the reduction affordable
+    uint32_t lg = 0;
+    while ((size_t(1) << (lg + 1)) <= B.n) lg++;
+    uint32_t c = window_bits ? (uint32_t)window_bits : std::min(20u, std::max(12u, lg));
     uint32_t nwin = (256 + c - 1) / c;
     if ((size_t)nwin * B.n >= (size_t(1) << 31)) return fail_arg(ctx, "precompute_bases: windows * n must be < 2^31");
     affine_t *table = nullptr;

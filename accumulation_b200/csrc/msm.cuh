@@ -150,52 +150,85 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_scan: exclusive scan of hist[0..nkeys) into offsets[0..nkeys] and cursor[0..nkeys); one CTA.
+// Exclusive scan of hist[0..nkeys) into offsets[0..nkeys] and cursor[0..nkeys).  Tiles of 4096 keys
+// (1024 threads x one 128-bit load).  Up to SCAN_ONE_CTA_TILES tiles a single CTA walks them serially
+// (k_scan); beyond that: k_scan_tile_sums -> k_scan over the tile sums -> k_scan_tiles.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t SCAN_TILE = 4096;
+constexpr uint32_t SCAN_ONE_CTA_TILES = 8;
+
+// exclusive scan of one tile starting at `carry`; returns the tile total (valid in every thread)
+ACC_D uint32_t scan_tile(const uint32_t *__restrict__ hist, uint32_t nkeys, uint32_t base, uint32_t carry,
+                         uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor, uint32_t *warp_sums,
+                         uint32_t *total_s) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t k0 = base + tid * 4;
+    uint32_t v[4];
+    if (k0 + 3 < nkeys) {
+        uint4 q = *reinterpret_cast<const uint4 *>(hist + k0);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (k0 + j < nkeys) ? hist[k0 + j] : 0u;
+    }
+    uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane];
+        uint32_t wi = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        warp_sums[lane] = wi - ws;  // exclusive prefix of warp sums
+        if (lane == 31) *total_s = wi;
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_sums[wid] + incl - tsum;
+    if (offsets) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (k0 + j < nkeys) { offsets[k0 + j] = excl; if (cursor) cursor[k0 + j] = excl; }
+            excl += v[j];
+        }
+    }
+    uint32_t total = *total_s;
+    __syncthreads();
+    return total;
+}
+
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict__ hist, uint32_t nkeys,
                                                 uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    // tiles of 1024 * 4 keys; each thread owns 4 consecutive keys of the tile (one 128-bit load)
-    for (uint32_t base = 0; base < nkeys; base += 4096) {
-        uint32_t k0 = base + tid * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = (k0 + j < nkeys) ? hist[k0 + j] : 0u;
-        uint32_t tsum = v[0] + v[1] + v[2] + v[3];
-        uint32_t incl = tsum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t ws = warp_sums[lane];
-            uint32_t wi = ws;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= d) wi += o;
-            }
-            warp_sums[lane] = wi - ws;  // exclusive prefix of warp sums
-        }
-        __syncthreads();
-        uint32_t excl = carry_s + warp_sums[wid] + incl - tsum;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (k0 + j < nkeys) { offsets[k0 + j] = excl; cursor[k0 + j] = excl; }
-            excl += v[j];
-        }
-        __syncthreads();
-        if (tid == 1023) carry_s = excl;
-        __syncthreads();
-    }
-    if (tid == 0) offsets[nkeys] = carry_s;
+    __shared__ uint32_t total_s;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nkeys; base += SCAN_TILE)
+        carry += scan_tile(hist, nkeys, base, carry, offsets, cursor, warp_sums, &total_s);
+    if (threadIdx.x == 0) offsets[nkeys] = carry;
+}
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(const uint32_t *__restrict__ hist, uint32_t nkeys,
+                                                          uint32_t *__restrict__ tile_sums) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total_s;
+    uint32_t total = scan_tile(hist, nkeys, blockIdx.x * SCAN_TILE, 0, nullptr, nullptr, warp_sums, &total_s);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// tile_offs = exclusive scan of the tile sums (ntiles + 1 entries, the last one is the grand total)
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict__ hist, uint32_t nkeys,
+                                                      const uint32_t *__restrict__ tile_offs, uint32_t *__restrict__ offsets,
+                                                      uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total_s;
+    scan_tile(hist, nkeys, blockIdx.x * SCAN_TILE, tile_offs[blockIdx.x], offsets, cursor, warp_sums, &total_s);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) offsets[nkeys] = tile_offs[gridDim.x];
 }
 
 // ------------------------------------------------------------------------------------------------

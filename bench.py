@@ -279,7 +279,7 @@ def main():
     value = n_total / (t_dev_ms * 1e-3) / 1e6
     e2e = n_total / (t_e2e_ms * 1e-3) / 1e6
     t_acc_ms = stage_acc.get("accumulate", 0.0) / args.steps
-    c = args.window_bits or (16 if not args.no_precompute else ctx_window_bits(count))
+    c = args.window_bits or (table_window_bits(count) if not args.no_precompute else ctx_window_bits(count))
     nwin = (256 + c - 1) // c
     out = {
         "metric": "Pallas MSM Mpts/s @2^20", "value": round(value, 3), "unit": "Mpts/s", "n_gpus": world, "steps": args.steps,
@@ -316,6 +316,11 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def table_window_bits(n):
+    """mirror of the automatic rule in accmsm_precompute_bases (reporting only)"""
+    return min(20, max(12, max(n, 1).bit_length() - 1))
 
 
 def ctx_window_bits(n):

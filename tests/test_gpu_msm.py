@@ -316,3 +316,21 @@ def test_precomputed_window_table(ctx, curve, c):
         assert ctx.ipa_check_final_key(B, ch, got[0], got[1])[0]
     finally:
         B.release()
+
+
+@pytest.mark.parametrize("c", [17, 20])
+def test_precomputed_wide_windows(ctx, c):
+    """window tables with c > 16 (more buckets than points per window; tiled multi-CTA scan)."""
+    N = 1 << 17
+    pts = cref.gen_points(0, 800 + c, N)
+    B = ctx.register_bases(0, pts).precompute(c)
+    try:
+        sc = cref.gen_scalars(cref.FQ, 801, N, True)
+        assert same_point(ctx.msm(B, sc), cref.commit(0, pts, sc))
+        n = (1 << 16) + 4321
+        sc = cref.gen_scalars(cref.FQ, 802, n, False)
+        assert same_point(ctx.msm(B, sc, montgomery=False, offset=999), cref.msm_ark(0, pts[999:999 + n], sc))
+        const = np.repeat(cref.gen_scalars(cref.FQ, 803, 1, True), N, axis=0)
+        assert same_point(ctx.msm(B, const), cref.commit(0, pts, const))
+    finally:
+        B.release()
