@@ -181,6 +181,30 @@ class Context:
                                                                C.c_size_t(coeff_offset), C.c_size_t(n), C.c_void_p(d_out_ptr),
                                                                C.c_void_p(stream)), "ipa_final_key_partial_dev")
 
+    # ---- IPA opening session
+    def ipa_open_begin(self, bases: "Bases", coeffs_mont, k: int, point_mont, h_prime_xy) -> int:
+        cf = _u64(coeffs_mont).reshape(-1, 4)
+        sess = C.c_uint64(0)
+        self._check(self._lib.accmsm_ipa_open_begin(self._h, C.c_uint64(bases.handle), _p(cf), C.c_size_t(cf.shape[0]), C.c_int(k),
+                                                    _p(_u64(point_mont)), _p(_u64(h_prime_xy)), C.byref(sess)), "ipa_open_begin")
+        return int(sess.value)
+
+    def ipa_open_round(self, session: int):
+        l, r = np.empty(8, dtype=np.uint64), np.empty(8, dtype=np.uint64)
+        li, ri = C.c_uint8(0), C.c_uint8(0)
+        self._check(self._lib.accmsm_ipa_open_round(self._h, C.c_uint64(session), _p(l), C.byref(li), _p(r), C.byref(ri)),
+                    "ipa_open_round")
+        return (l, int(li.value)), (r, int(ri.value))
+
+    def ipa_open_fold(self, session: int, xi_mont, xi_inv_mont):
+        self._check(self._lib.accmsm_ipa_open_fold(self._h, C.c_uint64(session), _p(_u64(xi_mont)), _p(_u64(xi_inv_mont))),
+                    "ipa_open_fold")
+
+    def ipa_open_finish(self, session: int):
+        fk, c = np.empty(8, dtype=np.uint64), np.empty(4, dtype=np.uint64)
+        self._check(self._lib.accmsm_ipa_open_finish(self._h, C.c_uint64(session), _p(fk), _p(c)), "ipa_open_finish")
+        return fk, c
+
     # ---- field-vector kernels
     def compute_coeffs(self, field: int, challenges_mont):
         ch = _u64(challenges_mont).reshape(-1, 4)

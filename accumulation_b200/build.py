@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libaccmsm.so")
 SOURCES = ["accmsm.cu"]
-DEPS = ["accmsm.cu", "vec_api.inc", "vec.cuh", "msm.cuh", "ec.cuh", "fp.cuh", os.path.join("..", "..", "include", "accmsm.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc"))) + [os.path.join("..", "..", "include", "accmsm.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550",

@@ -12,6 +12,7 @@
 #include "../../include/accmsm.h"
 #include "msm.cuh"
 #include "vec.cuh"
+#include "ipa.cuh"
 
 using namespace accmsm;
 
@@ -47,6 +48,9 @@ template <class T> struct DevBuf {
 
 }  // namespace
 
+struct IpaSession;
+void ipa_session_free(IpaSession *s);
+
 struct accmsm_ctx {
     int device = 0;
     int sm_count = 0;
@@ -54,6 +58,7 @@ struct accmsm_ctx {
     std::mutex mu;
     std::string last_error;
     std::unordered_map<uint64_t, Bases> bases;
+    std::unordered_map<uint64_t, struct IpaSession *> ipa_sessions;
     uint64_t next_handle = 1;
     int window_bits = 0;
     uint64_t launches = 0;
@@ -152,7 +157,9 @@ MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, size_t offset, size_t
 // either a device partial (d_partial) or the normalised affine result in ctx->d_out_affine/d_out_inf.
 template <int CURVE, class Src>
 int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src &src, const uint8_t *d_inf,
-            const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st) {
+            const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
+            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
+    if (!d_out_aff) { d_out_aff = ctx->d_out_affine; d_out_inf = ctx->d_out_inf; }
     MsmShape sh = make_shape(ctx, B, offset, n);
     const bool tabled = sh.ent_stride != 0;
     const uint32_t nsets = tabled ? 1u : sh.nwin;              // bucket sets to reduce and combine
@@ -244,7 +251,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
     }
     mark(ctx, ST_FINISH, st);
     k_finish<CURVE><<<1, 32, 0, st>>>(window_sums, nsets, sh.c, d_extra, n_extra, normalise ? 1 : 0, d_partial,
-                                      ctx->d_out_affine, ctx->d_out_inf);
+                                      d_out_aff, d_out_inf);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     return ACCMSM_OK;
@@ -373,6 +380,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
         if (kv.second.d_inf) cudaFree(kv.second.d_inf);
         if (kv.second.d_table) cudaFree(kv.second.d_table);
     }
+    for (auto &kv : ctx->ipa_sessions) ipa_session_free(kv.second);
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release();
@@ -673,3 +681,4 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
 }  // extern "C"
 
 #include "vec_api.inc"
+#include "ipa_api.inc"

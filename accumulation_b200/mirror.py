@@ -61,8 +61,47 @@ class SuccinctCheckPolynomial:
         return self.ctx.compute_coeffs(self.field, self.challenges)
 
 
+_MODULI = (0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001,   # Fp: Pallas base / Vesta scalar
+           0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001)   # Fq: Pallas scalar / Vesta base
+
+
+def _fe_to_int(field: int, mont) -> int:
+    """host-side scalar helper (one element per IPA round, like ark-ff on the Rust host): Montgomery limbs -> int"""
+    m = _MODULI[field]
+    v = sum(int(x) << (64 * i) for i, x in enumerate(np.asarray(mont, dtype=np.uint64).reshape(4)))
+    return v * pow(1 << 256, -1, m) % m
+
+
+def _int_to_fe(field: int, v: int) -> np.ndarray:
+    m = _MODULI[field]
+    w = (v % m) * (1 << 256) % m
+    return np.array([(w >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
 class InnerProductArgPC:
     """The parts of ark_poly_commit::ipa_pc::InnerProductArgPC that run the MSM."""
+
+    @staticmethod
+    def open(ck: CommitterKey, combined_coeffs, point, h_prime_xy, round_challenge, log_d: Optional[int] = None):
+        """Core of open_individual_opening_challenges (src/ipa_pc_as/mod.rs:454-462) after the
+        host has combined the polynomials and derived h' = xi_0 * h.  `round_challenge(prev_xi, l, r) -> xi` is the
+        host sponge (Montgomery limbs in and out; prev_xi is None in the first round).
+        Returns (l_vec, r_vec, final_comm_key_xy, c, challenges)."""
+        from . import scalar_field
+        ctx = ck.bases.ctx
+        field = scalar_field(ck.curve)
+        cf = np.ascontiguousarray(combined_coeffs, dtype=np.uint64).reshape(-1, 4)
+        k = log_d if log_d is not None else max(cf.shape[0] - 1, 0).bit_length()
+        sess = ctx.ipa_open_begin(ck.bases, cf, k, point, h_prime_xy)
+        l_vec, r_vec, challenges, xi = [], [], [], None
+        for _ in range(k):
+            l, r = ctx.ipa_open_round(sess)
+            xi = np.ascontiguousarray(round_challenge(xi, l, r), dtype=np.uint64).reshape(4)
+            xi_inv = _int_to_fe(field, pow(_fe_to_int(field, xi), -1, _MODULI[field]))
+            ctx.ipa_open_fold(sess, xi, xi_inv)
+            l_vec.append(l); r_vec.append(r); challenges.append(xi)
+        final_key, c = ctx.ipa_open_finish(sess)
+        return l_vec, r_vec, final_key, c, challenges
 
     @staticmethod
     def cm_commit(comm_key: CommitterKey, scalars, hiding_generator_index: Optional[int] = None, randomizer=None):

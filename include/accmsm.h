@@ -126,6 +126,24 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
                                      int k, size_t coeff_offset, size_t n, void *d_out_partial,
                                      void *stream);
 
+/* ---- IPA opening (IpaPC::open_individual_opening_challenges) ---------------------------
+ * Reference call sites: src/ipa_pc_as/mod.rs:454-462 (AtomicASForInnerProductArgPC::prove), :525-534 (index,
+ * default proof), examples/scaling-pc.rs:72-81.  The opening state (coefficients padded to D = 2^k, the
+ * z-vector (1, z, z^2, ..), the folded key) lives in HBM for the whole session; the host keeps the sponge:
+ *     begin(handle, combined_polynomial_coeffs, k, point, h' = xi_0 * h)
+ *     repeat k times:  round() -> (l, r);  xi = sponge(xi_prev, l, r);  fold(xi, xi^-1)
+ *     finish() -> (final_comm_key, c)
+ * round:  l = cm_commit(key_l, coeffs_r) + <coeffs_r, z_l> h'      r = cm_commit(key_r, coeffs_l) + <coeffs_l, z_r> h'
+ * fold :  coeffs_l += xi^-1 coeffs_r;  z_l += xi z_r;  key_l += xi key_r (batch-normalised)
+ * fold only enqueues; finish releases the session (also on error).  A folded generator equal to the identity
+ * (probability ~2^-255 for sponge challenges) is not representable and is not detected. */
+int accmsm_ipa_open_begin(accmsm_ctx *ctx, uint64_t handle, const uint64_t *coeffs_mont, size_t n_coeffs, int k,
+                          const uint64_t point_mont[4], const uint64_t h_prime_xy[8], uint64_t *session);
+int accmsm_ipa_open_round(accmsm_ctx *ctx, uint64_t session, uint64_t l_xy[8], uint8_t *l_inf,
+                          uint64_t r_xy[8], uint8_t *r_inf);
+int accmsm_ipa_open_fold(accmsm_ctx *ctx, uint64_t session, const uint64_t xi_mont[4], const uint64_t xi_inv_mont[4]);
+int accmsm_ipa_open_finish(accmsm_ctx *ctx, uint64_t session, uint64_t final_key_xy[8], uint64_t c_mont[4]);
+
 /* ---- field-vector kernels (K3 materialised, K4, K5); all pointers HOST, Montgomery images -------------- */
 /* SuccinctCheckPolynomial::compute_coeffs (src/ipa_pc_as/mod.rs:400): out = 2^k elements */
 int accmsm_compute_coeffs(accmsm_ctx *ctx, int field, const uint64_t *challenges_mont, int k, uint64_t *out);

@@ -195,6 +195,42 @@ def ipa_fold_key(curve, key_xy, challenges_mont):
     return out, int(oinf.value)
 
 
+def powers(field, z_mont, n):
+    z = _u64(z_mont)
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().oracle_powers(C.c_int(field), _p(z), C.c_size_t(n), _p(out))
+    return out
+
+
+def ipa_open_round_lr(curve, key_xy, coeffs_mont, z_vec_mont, h_prime_xy):
+    key_xy, cf, zv, hp = _u64(key_xy), _u64(coeffs_mont), _u64(z_vec_mont), _u64(h_prime_xy)
+    n = cf.size // 4
+    l, r = np.empty(8, dtype=np.uint64), np.empty(8, dtype=np.uint64)
+    li, ri = C.c_uint8(0), C.c_uint8(0)
+    lib().oracle_ipa_open_round_lr(C.c_int(curve), _p(key_xy), _p(cf), _p(zv), C.c_size_t(n), _p(hp), _p(l), C.byref(li),
+                                   _p(r), C.byref(ri))
+    return (l, int(li.value)), (r, int(ri.value))
+
+
+def ipa_open_fold(curve, key_xy, coeffs_mont, z_vec_mont, xi_mont, xi_inv_mont):
+    """in place on copies; returns the folded (key, coeffs, z) halves"""
+    key, cf, zv = _u64(key_xy).copy(), _u64(coeffs_mont).copy(), _u64(z_vec_mont).copy()
+    n = cf.size // 4
+    xi, xinv = _u64(xi_mont), _u64(xi_inv_mont)
+    lib().oracle_ipa_open_fold(C.c_int(curve), _p(key), _p(cf), _p(zv), C.c_size_t(n), _p(xi), _p(xinv))
+    h = n // 2
+    return key.reshape(-1, 8)[:h].copy(), cf.reshape(-1, 4)[:h].copy(), zv.reshape(-1, 4)[:h].copy()
+
+
+def ipa_succinct_check(curve, comm, z_mont, v_mont, l_xy, r_xy, xi_mont, h_prime_xy, final_key_xy, c_mont) -> bool:
+    comm_xy, comm_inf = comm
+    l_xy, r_xy, xi = _u64(l_xy), _u64(r_xy), _u64(xi_mont)
+    k = xi.size // 4
+    return bool(lib().oracle_ipa_succinct_check(C.c_int(curve), _p(_u64(comm_xy)), C.c_uint8(int(comm_inf)), _p(_u64(z_mont)),
+                                                _p(_u64(v_mont)), _p(l_xy), _p(r_xy), C.c_int(k), _p(xi), _p(_u64(h_prime_xy)),
+                                                _p(_u64(final_key_xy)), _p(_u64(c_mont))))
+
+
 def combine_check_polys(field, challenges_mont, alphas_mont, random_poly_mont=None):
     ch = _u64(challenges_mont)           # (m, k, 4)
     m, k = ch.shape[0], ch.shape[1]

@@ -535,6 +535,84 @@ void oracle_ipa_fold_key(int curve, const uint64_t *key_xy, size_t n_key, const 
     memcpy(out_xy, cur, 64); *out_inf = inf[0];
     free(cur); free(inf);
 }
+/* ---------------------------------------------------------------- IpaPC::open / succinct_check
+ * (ark-poly-commit ipa_pc; reference call sites src/ipa_pc_as/mod.rs:454-462 (prove),
+ * :525-534 (index default proof), :198-205 (succinct_check), examples/scaling-pc.rs:72-81).  The round
+ * challenges come from the host sponge, so the restatement is per round: the caller squeezes xi from
+ * (l, r) between oracle_ipa_open_round_lr and oracle_ipa_open_fold. */
+static void inner_product(const field_t *S, const uint64_t *a, const uint64_t *b, size_t n, fe *out) {
+    fe acc; memset(&acc, 0, sizeof acc);
+    for (size_t i = 0; i < n; i++) { fe t; f_mul(S, &t, FE(a, i), FE(b, i)); f_add(S, &acc, &acc, &t); }
+    *out = acc;
+}
+/* z_vec = (1, z, z^2, ...) */
+void oracle_powers(int f, const uint64_t *z, size_t n, uint64_t *out) {
+    const field_t *F = field_of(f);
+    fe cur = F->r;
+    for (size_t i = 0; i < n; i++) { *FEO(out, i) = cur; f_mul(F, &cur, &cur, (const fe *)z); }
+}
+/* state: key (n points, affine), coeffs (n), z (n); n even.
+ *   l = cm_commit(key_l, coeffs_r) + <coeffs_r, z_l> h'      r = cm_commit(key_r, coeffs_l) + <coeffs_l, z_r> h' */
+void oracle_ipa_open_round_lr(int curve, const uint64_t *key_xy, const uint64_t *coeffs,
+                              const uint64_t *z, size_t n, const uint64_t *h_prime_xy,
+                              uint64_t *l_xy, uint8_t *l_inf, uint64_t *r_xy, uint8_t *r_inf) {
+    const field_t *S = scalar_field(curve);
+    size_t h = n / 2;
+    fe ipl, ipr;
+    inner_product(S, coeffs + 4 * h, z, h, &ipl);
+    inner_product(S, coeffs, z + 4 * h, h, &ipr);
+    oracle_commit(curve, key_xy, h, coeffs + 4 * h, h, h_prime_xy, ipl.l, l_xy, l_inf);
+    oracle_commit(curve, key_xy + 8 * h, h, coeffs, h, h_prime_xy, ipr.l, r_xy, r_inf);
+}
+/* coeffs_l += xi^-1 coeffs_r ; z_l += xi z_r ; key_l += xi key_r (normalised); the first n/2 entries hold
+ * the folded state afterwards */
+void oracle_ipa_open_fold(int curve, uint64_t *key_xy, uint64_t *coeffs, uint64_t *z, size_t n,
+                          const uint64_t *xi_mont, const uint64_t *xi_inv_mont) {
+    const field_t *F = base_field(curve), *S = scalar_field(curve);
+    size_t h = n / 2;
+    fe xi; f_from_mont(S, &xi, (const fe *)xi_mont);
+#pragma omp parallel for
+    for (size_t i = 0; i < h; i++) {
+        fe t;
+        f_mul(S, &t, (const fe *)xi_inv_mont, FE(coeffs, i + h)); f_add(S, FEO(coeffs, i), FE(coeffs, i), &t);
+        f_mul(S, &t, (const fe *)xi_mont, FE(z, i + h)); f_add(S, FEO(z, i), FE(z, i), &t);
+        aff l, rr; load_aff(&l, key_xy + 8 * i, 0); load_aff(&rr, key_xy + 8 * (i + h), 0);
+        jac p; j_mul(F, &p, &rr, &xi); j_add_mixed(F, &p, &l);
+        uint8_t inf; j_to_affine(F, &p, key_xy + 8 * i, &inf);
+    }
+}
+/* succinct_check's group equation with the transcript values given:
+ *   C' = C + v h' + sum_i (xi_i^-1 l_i + xi_i r_i) ;  accept iff C' == c final_key + (h(z) c) h' */
+int oracle_ipa_succinct_check(int curve, const uint64_t *comm_xy, uint8_t comm_inf, const uint64_t *z,
+                              const uint64_t *v, const uint64_t *l_xy, const uint64_t *r_xy, int k,
+                              const uint64_t *xi_mont, const uint64_t *h_prime_xy,
+                              const uint64_t *final_key_xy, const uint64_t *c_mont) {
+    const field_t *F = base_field(curve), *S = scalar_field(curve);
+    int sf = curve == 0 ? 1 : 0;
+    jac acc; j_zero(F, &acc);
+    aff a; load_aff(&a, comm_xy, comm_inf);
+    if (!comm_inf) j_add_mixed(F, &acc, &a);
+    aff hp; load_aff(&hp, h_prime_xy, 0);
+    fe s; jac t;
+    f_from_mont(S, &s, (const fe *)v); j_mul(F, &t, &hp, &s); j_add(F, &acc, &t);
+    for (int i = 0; i < k; i++) {
+        fe xinv; f_inv(S, &xinv, FE(xi_mont, i));
+        aff l, r; load_aff(&l, l_xy + 8 * i, 0); load_aff(&r, r_xy + 8 * i, 0);
+        f_from_mont(S, &s, &xinv); j_mul(F, &t, &l, &s); j_add(F, &acc, &t);
+        f_from_mont(S, &s, FE(xi_mont, i)); j_mul(F, &t, &r, &s); j_add(F, &acc, &t);
+    }
+    uint64_t hz[4]; oracle_succinct_evaluate(sf, xi_mont, k, z, hz);
+    fe vp; f_mul(S, &vp, (const fe *)hz, (const fe *)c_mont);
+    jac rhs; j_zero(F, &rhs);
+    aff fk; load_aff(&fk, final_key_xy, 0);
+    f_from_mont(S, &s, (const fe *)c_mont); j_mul(F, &t, &fk, &s); j_add(F, &rhs, &t);
+    f_from_mont(S, &s, &vp); j_mul(F, &t, &hp, &s); j_add(F, &rhs, &t);
+    uint64_t a_xy[8], b_xy[8]; uint8_t a_inf, b_inf;
+    j_to_affine(F, &acc, a_xy, &a_inf); j_to_affine(F, &rhs, b_xy, &b_inf);
+    if (a_inf || b_inf) return a_inf == b_inf;
+    return memcmp(a_xy, b_xy, 64) == 0;
+}
+
 void oracle_combine_check_polys(int f, const uint64_t *ch, int m, int k, const uint64_t *alphas,
                                 const uint64_t *random_poly, size_t n_random, uint64_t *out) {
     const field_t *F = field_of(f);

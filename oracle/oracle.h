@@ -62,6 +62,20 @@ int  oracle_ipa_check_final_key(int curve, const uint64_t *key_xy, size_t n_key,
 /* key folding of IpaPC::open (App. A.2): key_l += xi_round * key_r, k rounds -> 1 point */
 void oracle_ipa_fold_key(int curve, const uint64_t *key_xy, size_t n_key,
                          const uint64_t *challenges_mont, int k, uint64_t *out_xy, uint8_t *out_inf);
+/* IpaPC::open, one round at a time (App. A.2; src/ipa_pc_as/mod.rs:454-462): the host squeezes the round
+ * challenge from (l, r) between the two calls.  State arrays hold n entries; after fold the first n/2 are live. */
+void oracle_powers(int field, const uint64_t *z_mont, size_t n, uint64_t *out_mont);
+void oracle_ipa_open_round_lr(int curve, const uint64_t *key_xy, const uint64_t *coeffs_mont,
+                              const uint64_t *z_vec_mont, size_t n, const uint64_t *h_prime_xy,
+                              uint64_t *l_xy, uint8_t *l_inf, uint64_t *r_xy, uint8_t *r_inf);
+void oracle_ipa_open_fold(int curve, uint64_t *key_xy, uint64_t *coeffs_mont, uint64_t *z_vec_mont, size_t n,
+                          const uint64_t *xi_mont, const uint64_t *xi_inv_mont);
+/* group equation of IpaPC::succinct_check (src/ipa_pc_as/mod.rs:198-205) with transcript values supplied */
+int  oracle_ipa_succinct_check(int curve, const uint64_t *comm_xy, uint8_t comm_inf, const uint64_t *z_mont,
+                               const uint64_t *v_mont, const uint64_t *l_xy, const uint64_t *r_xy, int k,
+                               const uint64_t *xi_mont, const uint64_t *h_prime_xy,
+                               const uint64_t *final_key_xy, const uint64_t *c_mont);
+
 /* combine_succinct_check_polynomials (src/ipa_pc_as/mod.rs:391-404) */
 void oracle_combine_check_polys(int field, const uint64_t *challenges_mont /* m x k */, int m, int k,
                                 const uint64_t *alphas_mont /* m */,

@@ -282,3 +282,33 @@ def fold_key(key, challenges, curve: int):
         key = [add(key[i], mul(xi, key[i + h], curve), curve) for i in range(h)]
     assert len(key) == 1
     return key[0]
+
+
+# --- IpaPC::open / succinct_check (src/ipa_pc_as/mod.rs:198-205,454-462) ------
+def ipa_open(key, coeffs, z: int, h_prime, challenges, curve: int):
+    """k rounds with the round challenges given (the host sponge squeezes them from (l, r) in the real
+    protocol).  Returns (l_vec, r_vec, final_comm_key, c)."""
+    q = scalar_modulus(curve)
+    key, a = list(key), [c % q for c in coeffs]
+    b = [pow(z, i, q) for i in range(len(a))]
+    l_vec, r_vec = [], []
+    for xi in challenges:
+        h = len(a) // 2
+        ip_l = sum(x * y for x, y in zip(a[h:], b[:h])) % q
+        ip_r = sum(x * y for x, y in zip(a[:h], b[h:])) % q
+        l_vec.append(add(msm_naive(key[:h], a[h:], curve), mul(ip_l, h_prime, curve), curve))
+        r_vec.append(add(msm_naive(key[h:], a[:h], curve), mul(ip_r, h_prime, curve), curve))
+        xinv = pow(xi, -1, q)
+        a = [(a[i] + xinv * a[i + h]) % q for i in range(h)]
+        b = [(b[i] + xi * b[i + h]) % q for i in range(h)]
+        key = [add(key[i], mul(xi, key[i + h], curve), curve) for i in range(h)]
+    return l_vec, r_vec, key[0], a[0]
+
+
+def ipa_succinct_check(comm, z: int, v: int, l_vec, r_vec, challenges, h_prime, final_key, c: int, curve: int) -> bool:
+    q = scalar_modulus(curve)
+    acc = add(comm, mul(v % q, h_prime, curve), curve)
+    for xi, l, r in zip(challenges, l_vec, r_vec):
+        acc = add(acc, add(mul(pow(xi, -1, q), l, curve), mul(xi, r, curve), curve), curve)
+    v_prime = succinct_evaluate(challenges, z, q) * c % q
+    return acc == add(mul(c, final_key, curve), mul(v_prime, h_prime, curve), curve)

@@ -75,6 +75,31 @@ def ipa_cases():
     return out
 
 
+def ipa_open_cases():
+    """IpaPC::open with fixed round challenges (k = 1, 3, 4): l_vec, r_vec, final_comm_key, c; the proof must
+    satisfy succinct_check's group equation and final_comm_key must equal MSM(key, compute_coeffs(xi))."""
+    out = []
+    for curve in (R.PALLAS, R.VESTA):
+        q = R.scalar_modulus(curve)
+        rng = R.SplitMix64(0xACC7 + curve)
+        for k in (1, 3, 4):
+            n = 1 << k
+            key = [R.random_point(rng, curve) for _ in range(n)]
+            h_prime = R.random_point(rng, curve)
+            coeffs = [rng.field(q) for _ in range(n)]
+            z = rng.field(q)
+            ch = [rng.field(q) for _ in range(k)]
+            l_vec, r_vec, final_key, c = R.ipa_open(key, coeffs, z, h_prime, ch, curve)
+            comm = R.msm_naive(key, coeffs, curve)
+            v = R.horner(coeffs, z, q)
+            assert R.ipa_succinct_check(comm, z, v, l_vec, r_vec, ch, h_prime, final_key, c, curve)
+            assert final_key == R.msm_naive(key, R.compute_coeffs(ch, q), curve)
+            out.append({"curve": curve, "k": k, "key": [pt(p) for p in key], "h_prime": pt(h_prime), "coeffs": [hx(x) for x in coeffs],
+                        "z": hx(z), "challenges": [hx(x) for x in ch], "l_vec": [pt(p) for p in l_vec], "r_vec": [pt(p) for p in r_vec],
+                        "final_key": pt(final_key), "c": hx(c), "comm": pt(comm), "v": hx(v)})
+    return out
+
+
 def vec_cases():
     out = []
     for field, m in ((0, R.P_PALLAS_BASE), (1, R.Q_PALLAS_SCALAR)):
@@ -109,7 +134,10 @@ def vec_cases():
 
 
 if __name__ == "__main__":
-    for name, fn in (("msm", msm_cases), ("ipa", ipa_cases), ("vec", vec_cases)):
+    only = sys.argv[1:]
+    for name, fn in (("msm", msm_cases), ("ipa", ipa_cases), ("vec", vec_cases), ("ipa_open", ipa_open_cases)):
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, f"{name}.json")
         with open(path, "w") as f:
             json.dump(fn(), f, indent=0, separators=(",", ":"))

@@ -140,3 +140,56 @@ def test_msm_algebraic_identities(curve):
     for i, v in enumerate(fe_ints(sf, rp)):
         exp[i] = (exp[i] + v) % q
     assert fe_ints(sf, comb) == exp
+
+
+def _ipa_open_with_oracle(curve, key, coeffs, z, h_prime, challenges):
+    """drives the per-round C oracle exactly like the GPU session is driven"""
+    sf = cref.scalar_field(curve)
+    zv = cref.powers(sf, z, coeffs.shape[0])
+    l_vec, r_vec = [], []
+    for xi in challenges:
+        l, r = cref.ipa_open_round_lr(curve, key, coeffs, zv, h_prime)
+        l_vec.append(l); r_vec.append(r)
+        key, coeffs, zv = cref.ipa_open_fold(curve, key, coeffs, zv, xi, cref.fe_inv(sf, xi.reshape(1, 4)).reshape(4))
+    return l_vec, r_vec, key[0], coeffs[0]
+
+
+def test_ipa_open_golden_vectors():
+    for case in load_golden("ipa_open"):
+        curve, k = case["curve"], case["k"]
+        sf = cref.scalar_field(curve)
+        key = points_mont(curve, case["key"])
+        hp = points_mont(curve, [case["h_prime"]]).reshape(8)
+        coeffs = fe_mont(sf, ints(case["coeffs"]))
+        z = fe_mont(sf, [int(case["z"], 16)]).reshape(4)
+        ch = fe_mont(sf, ints(case["challenges"]))
+        l_vec, r_vec, fk, c = _ipa_open_with_oracle(curve, key, coeffs, z, hp, ch)
+        for got, exp in zip(l_vec, case["l_vec"]):
+            assert same_point(got, point_result(curve, exp))
+        for got, exp in zip(r_vec, case["r_vec"]):
+            assert same_point(got, point_result(curve, exp))
+        assert same_point((fk, 0), point_result(curve, case["final_key"]))
+        assert fe_ints(sf, c.reshape(1, 4)) == [int(case["c"], 16)]
+        comm = point_result(curve, case["comm"])
+        v = fe_mont(sf, [int(case["v"], 16)]).reshape(4)
+        lx = np.array([p[0] for p in l_vec]); rx = np.array([p[0] for p in r_vec])
+        assert cref.ipa_succinct_check(curve, comm, z, v, lx, rx, ch, hp, fk, c)
+        bad = c.copy(); bad[0] ^= np.uint64(1)
+        assert not cref.ipa_succinct_check(curve, comm, z, v, lx, rx, ch, hp, fk, bad)
+
+
+def test_ipa_open_larger_self_consistency():
+    """k = 7: proof from the restated open verifies under succinct_check and final_key == MSM(key, h coeffs)."""
+    curve, k = 0, 7
+    sf = cref.scalar_field(curve)
+    n = 1 << k
+    key = cref.gen_points(curve, 31, n + 1)
+    hp, key = key[n], key[:n]
+    coeffs = cref.gen_scalars(sf, 32, n, True)
+    z = cref.gen_scalars(sf, 33, 1, True).reshape(4)
+    ch = cref.gen_scalars(sf, 34, k, True)
+    l_vec, r_vec, fk, c = _ipa_open_with_oracle(curve, key, coeffs, z, hp, ch)
+    comm = cref.commit(curve, key, coeffs)
+    v = cref.poly_evaluate(sf, coeffs, z)
+    assert cref.ipa_succinct_check(curve, comm, z, v, np.array([p[0] for p in l_vec]), np.array([p[0] for p in r_vec]), ch, hp, fk, c)
+    assert same_point((fk, 0), cref.commit(curve, key, cref.compute_coeffs(sf, ch)))
