@@ -130,41 +130,50 @@ bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
     return n >= (size_t(1) << (B.pre_c > 4 ? B.pre_c - 4 : 0));
 }
 
-MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n) {
+struct MsmJobs {
+    uint32_t njobs = 1;
+    size_t offset[MAX_JOBS] = {0};     // first base of every job inside the key
+    MsmJobs() {}
+    explicit MsmJobs(size_t off) { offset[0] = off; }
+};
+
+MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n) {
     MsmShape sh;
     sh.n = (uint32_t)n;
+    sh.njobs = jobs.njobs;
+    for (int j = 0; j < MAX_JOBS; j++) sh.job_off[j] = j < (int)jobs.njobs ? (uint32_t)jobs.offset[j] : 0u;
     if (use_table(ctx, B, n)) {
         sh.c = B.pre_c;
         sh.nwin = B.pre_nwin;
         sh.nb = 1u << (sh.c - 1);
-        sh.nkeys = sh.nb;
+        sh.sets_per_job = 1;
         sh.hist_stride = 0;
         sh.ent_stride = (uint32_t)B.n;
-        sh.ent_offset = (uint32_t)offset;
     } else {
         sh.c = pick_window_bits(ctx, n);
         sh.nwin = (256 + sh.c - 1) / sh.c;
         sh.nb = 1u << (sh.c - 1);
-        sh.nkeys = sh.nwin * sh.nb;
+        sh.sets_per_job = sh.nwin;
         sh.hist_stride = sh.nb;
         sh.ent_stride = 0;
-        sh.ent_offset = 0;
     }
+    sh.nkeys = sh.njobs * sh.sets_per_job * sh.nb;
     return sh;
 }
 
 // The MSM pipeline after the digits kernel has been chosen.  Leaves the per-window sums combined into
 // either a device partial (d_partial) or the normalised affine result in ctx->d_out_affine/d_out_inf.
 template <int CURVE, class Src>
-int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src &src, const uint8_t *d_inf,
+int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const Src &src,
             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
             affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
     if (!d_out_aff) { d_out_aff = ctx->d_out_affine; d_out_inf = ctx->d_out_inf; }
-    MsmShape sh = make_shape(ctx, B, offset, n);
+    MsmShape sh = make_shape(ctx, B, jobs, n);
     const bool tabled = sh.ent_stride != 0;
-    const uint32_t nsets = tabled ? 1u : sh.nwin;              // bucket sets to reduce and combine
-    const affine_t *points = tabled ? B.d_table : B.d_xy + offset;
-    const size_t n_entries = (size_t)sh.n * sh.nwin;
+    const uint32_t nsets = sh.njobs * sh.sets_per_job;          // bucket sets to reduce
+    const affine_t *points = tabled ? B.d_table : B.d_xy;
+    const size_t n_entries = (size_t)sh.n * sh.nwin * sh.njobs;
+    if (n_entries >= (size_t(1) << 31)) return fail_arg(ctx, "msm: jobs * windows * n must be < 2^31");
     CU(ctx, ctx->digits.ensure(n_entries));
     CU(ctx, ctx->entries.ensure(n_entries));
     CU(ctx, ctx->hist.ensure(sh.nkeys));
@@ -175,8 +184,8 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
     mark(ctx, ST_DIGITS, st);
     CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), st));
     {
-        uint32_t blocks = (sh.n + 255) / 256;
-        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, d_inf, ctx->digits.p, ctx->hist.p);
+        dim3 blocks((sh.n + 255) / 256, sh.njobs);
+        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p);
         ctx->launches++;
     }
     mark(ctx, ST_SCAN, st);
@@ -196,7 +205,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
     }
     mark(ctx, ST_SCATTER, st);
     {
-        uint32_t blocks = (sh.n + 255) / 256;
+        dim3 blocks((sh.n + 255) / 256, sh.njobs);
         k_scatter<<<blocks, 256, 0, st>>>(sh, ctx->digits.p, ctx->cursor.p, ctx->entries.p);
         ctx->launches++;
     }
@@ -250,11 +259,29 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const Src 
         window_sums = ctx->red_wsum[cur].p;
     }
     mark(ctx, ST_FINISH, st);
-    k_finish<CURVE><<<1, 32, 0, st>>>(window_sums, nsets, sh.c, d_extra, n_extra, normalise ? 1 : 0, d_partial,
-                                      d_out_aff, d_out_inf);
+    k_finish<CURVE><<<sh.njobs, 32, 0, st>>>(window_sums, sh.sets_per_job, sh.c, d_extra, n_extra, normalise ? 1 : 0,
+                                             d_partial, d_out_aff, d_out_inf);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     return ACCMSM_OK;
+}
+
+// run_msm over scalar vectors resident in HBM (one pointer per job), dispatched on the key's curve
+int msm_mem(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const uint8_t *const *d_scalars, int mont,
+            const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
+            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
+    if (B.curve == 0) {
+        MemScalars<1> src; src.montgomery = mont;
+        for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
+        return run_msm<0>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+    }
+    MemScalars<0> src; src.montgomery = mont;
+    for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
+    return run_msm<1>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+}
+int msm_mem1(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint8_t *d_scalars, int mont,
+             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st) {
+    return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st);
 }
 
 // normalised result -> host
@@ -294,15 +321,7 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
     CU(ctx, ctx->scalars.ensure(n * 32));
     mark(ctx, ST_H2D, st);
     CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    const uint8_t *d_inf = B.d_inf ? B.d_inf + offset : nullptr;
-    int rc;
-    if (B.curve == 0) {
-        MemScalars<1> src{ctx->scalars.p, mont};
-        rc = run_msm<0>(ctx, B, offset, n, src, d_inf, d_extra, n_extra, nullptr, true, st);
-    } else {
-        MemScalars<0> src{ctx->scalars.p, mont};
-        rc = run_msm<1>(ctx, B, offset, n, src, d_inf, d_extra, n_extra, nullptr, true, st);
-    }
+    int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, nullptr, true, st);
     if (rc) return rc;
     return fetch_affine(ctx, out_xy, out_inf, st);
 }
@@ -342,9 +361,9 @@ int accmsm_init(accmsm_ctx **out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
     for (int i = 0; i <= ST_COUNT; i++) { cudaEventCreate(&ctx->ev[i]); ctx->ev_valid[i] = false; }
-    bool ok = cudaMalloc(&ctx->d_out_affine, sizeof(affine_t)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_out_inf, 16) == cudaSuccess &&
-              cudaMallocHost(&ctx->h_out, 32 * sizeof(uint64_t)) == cudaSuccess;
+    bool ok = cudaMalloc(&ctx->d_out_affine, MAX_JOBS * sizeof(affine_t)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_out_inf, MAX_JOBS * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_out, (MAX_JOBS * 9 + 32) * sizeof(uint64_t)) == cudaSuccess;
     // shared-memory opt-in and resident CTAs per SM for the accumulate kernels
     size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
     size_t smem_fix = (size_t)FIX_THREADS * FIX_PER_T * (sizeof(xyzz_t) + sizeof(uint32_t));
@@ -525,11 +544,37 @@ int accmsm_msm(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const 
 
 int accmsm_msm_batch(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars,
                      int scalars_montgomery, uint64_t *out_xy, uint8_t *out_inf) {
-    if (!ctx || !out_xy || !out_inf || (n && k && !scalars)) return fail_arg(ctx, "msm_batch: bad argument");
-    for (size_t j = 0; j < k; j++) {
-        int rc = accmsm_msm(ctx, handle, offset, n, scalars + j * n * 4, scalars_montgomery, out_xy + 8 * j, out_inf + j);
+    if (!ctx || (k && (!out_xy || !out_inf)) || (n && k && !scalars)) return fail_arg(ctx, "msm_batch: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "msm_batch: range exceeds registered bases");
+    if (n == 0) { for (size_t j = 0; j < k; j++) write_identity(ctx, B->curve, out_xy + 8 * j, out_inf + j); return ACCMSM_OK; }
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // all k scalar vectors go up in one copy; groups of MAX_JOBS share one pass of the pipeline (one sort,
+    // one accumulation over all their bucket sets, one reduction, one finish launch)
+    clear_marks(ctx);
+    CU(ctx, ctx->scalars.ensure(n * k * 32));
+    mark(ctx, ST_H2D, st);
+    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * k * 32, cudaMemcpyHostToDevice, st));
+    for (size_t j0 = 0; j0 < k; j0 += MAX_JOBS) {
+        MsmJobs jobs;
+        jobs.njobs = (uint32_t)std::min<size_t>(MAX_JOBS, k - j0);
+        const uint8_t *ptrs[MAX_JOBS];
+        for (uint32_t j = 0; j < jobs.njobs; j++) { jobs.offset[j] = offset; ptrs[j] = ctx->scalars.p + (j0 + j) * n * 32; }
+        int rc = msm_mem(ctx, *B, jobs, n, ptrs, scalars_montgomery, nullptr, 0, nullptr, true, st);
         if (rc) return rc;
+        mark(ctx, ST_D2H, st);
+        CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, jobs.njobs * 64, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(ctx->h_out + 8 * MAX_JOBS, ctx->d_out_inf, jobs.njobs * 4, cudaMemcpyDeviceToHost, st));
+        mark(ctx, ST_COUNT, st);
+        CU(ctx, cudaStreamSynchronize(st));
+        memcpy(out_xy + 8 * j0, ctx->h_out, jobs.njobs * 64);
+        const uint32_t *inf = (const uint32_t *)(ctx->h_out + 8 * MAX_JOBS);
+        for (uint32_t j = 0; j < jobs.njobs; j++) out_inf[j0 + j] = inf[j] != 0;
     }
+    collect_timings(ctx);
     return ACCMSM_OK;
 }
 
@@ -548,10 +593,7 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
     CU(ctx, ctx->scalars.ensure(std::max<size_t>(n, 1) * 32));
     clear_marks(ctx);
     CU(ctx, cudaMemcpyAsync(ctx->scalars.p, randomizer_mont, 32, cudaMemcpyHostToDevice, st));
-    int rc;
-    const uint8_t *d_inf1 = B->d_inf ? B->d_inf + hiding_index : nullptr;
-    if (B->curve == 0) { MemScalars<1> s1{ctx->scalars.p, 1}; rc = run_msm<0>(ctx, *B, hiding_index, 1, s1, d_inf1, nullptr, 0, ctx->partial.p, false, st); }
-    else { MemScalars<0> s1{ctx->scalars.p, 1}; rc = run_msm<1>(ctx, *B, hiding_index, 1, s1, d_inf1, nullptr, 0, ctx->partial.p, false, st); }
+    int rc = msm_mem1(ctx, *B, hiding_index, 1, ctx->scalars.p, 1, nullptr, 0, ctx->partial.p, false, st);
     if (rc) return rc;
     if (n == 0) {
         if (B->curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, ctx->partial.p, 1, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
@@ -573,10 +615,7 @@ int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, co
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     clear_marks(ctx);
-    const uint8_t *d_inf = B->d_inf ? B->d_inf + offset : nullptr;
-    int rc;
-    if (B->curve == 0) { MemScalars<1> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<0>(ctx, *B, offset, n, src, d_inf, nullptr, 0, nullptr, true, st); }
-    else { MemScalars<0> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<1>(ctx, *B, offset, n, src, d_inf, nullptr, 0, nullptr, true, st); }
+    int rc = msm_mem1(ctx, *B, offset, n, (const uint8_t *)d_scalars, scalars_montgomery, nullptr, 0, nullptr, true, st);
     if (rc) return rc;
     return fetch_affine(ctx, out_xy, out_inf, st);
 }
@@ -598,9 +637,7 @@ int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size
         ctx->launches++;
         rc = ACCMSM_OK;
     } else {
-        const uint8_t *d_inf = B->d_inf ? B->d_inf + offset : nullptr;
-        if (B->curve == 0) { MemScalars<1> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<0>(ctx, *B, offset, n, src, d_inf, nullptr, 0, (xyzz_t *)d_out_partial, false, st); }
-        else { MemScalars<0> src{(const uint8_t *)d_scalars, scalars_montgomery}; rc = run_msm<1>(ctx, *B, offset, n, src, d_inf, nullptr, 0, (xyzz_t *)d_out_partial, false, st); }
+        rc = msm_mem1(ctx, *B, offset, n, (const uint8_t *)d_scalars, scalars_montgomery, nullptr, 0, (xyzz_t *)d_out_partial, false, st);
     }
     if (rc) return rc;
     mark(ctx, ST_COUNT, st);
@@ -626,9 +663,9 @@ static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_m
                    xyzz_t *d_partial, bool normalise, cudaStream_t st) {
     CU(ctx, ctx->misc.ensure(64 * 32));
     if (k) CU(ctx, cudaMemcpyAsync(ctx->misc.p, challenges_mont, (size_t)k * 32, cudaMemcpyHostToDevice, st));
-    if (B.curve == 0) { IpaScalars<1> src{ctx->misc.p, k, (uint32_t)coeff_offset}; return run_msm<0>(ctx, B, 0, n, src, B.d_inf, nullptr, 0, d_partial, normalise, st); }
+    if (B.curve == 0) { IpaScalars<1> src{ctx->misc.p, k, (uint32_t)coeff_offset}; return run_msm<0>(ctx, B, MsmJobs(0), n, src, nullptr, 0, d_partial, normalise, st); }
     IpaScalars<0> src{ctx->misc.p, k, (uint32_t)coeff_offset};
-    return run_msm<1>(ctx, B, 0, n, src, B.d_inf, nullptr, 0, d_partial, normalise, st);
+    return run_msm<1>(ctx, B, MsmJobs(0), n, src, nullptr, 0, d_partial, normalise, st);
 }
 
 int accmsm_ipa_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k, uint64_t out_xy[8],

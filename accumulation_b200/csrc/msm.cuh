@@ -27,6 +27,7 @@ constexpr int FIX_THREADS = 512;       // k_fixup: one CTA, FIX_PER_T slots per 
 constexpr int FIX_PER_T = 3;
 constexpr int RED0_SEG = 16;           // buckets per thread in the first reduction level
 constexpr int MAX_WINDOWS = 64;
+constexpr int MAX_JOBS = 8;            // MSMs that share one pass of the pipeline (same key, same length)
 
 struct MsmShape {
     uint32_t n;        // number of (base, scalar) pairs
@@ -39,7 +40,13 @@ struct MsmShape {
     // (hist_stride = 0) and an entry indexes the table: w * ent_stride + ent_offset + i.
     uint32_t hist_stride;
     uint32_t ent_stride;
-    uint32_t ent_offset;
+    // Batch: njobs MSMs of the same length over (possibly different) ranges of one key go through the
+    // pipeline together -- hp_as::decide commits a, b, a o b (src/hp_as/mod.rs:910-918), the NARK commits
+    // z_A, z_B, z_C (src/r1cs_nark_as/r1cs_nark/mod.rs:216-218), an IPA round its (l, r) pair.  Job j owns
+    // bucket sets [j * sets_per_job, (j + 1) * sets_per_job) and reads bases job_off[j] + i.
+    uint32_t njobs;
+    uint32_t sets_per_job;   // nwin (plain key) or 1 (window table)
+    uint32_t job_off[MAX_JOBS];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -84,10 +91,10 @@ ACC_D void store_xyzz(xyzz_t *p, const xyzz_t &r) {
 // Scalars resident in HBM: n x 32 B, either the Fp256 Montgomery image (what PedersenCommitment::commit
 // receives; into_repr() is done here) or canonical BigInteger256 (what VariableBaseMSM receives).
 template <int SFIELD> struct MemScalars {
-    const uint8_t *ptr;
+    const uint8_t *ptr[MAX_JOBS];
     int montgomery;
-    ACC_D fe_t canonical(uint32_t i) const {
-        fe_t s = load_fe_nc(ptr + (size_t)i * 32);
+    ACC_D fe_t canonical(uint32_t job, uint32_t i) const {
+        fe_t s = load_fe_nc(ptr[job] + (size_t)i * 32);
         if (montgomery) s = Fp<SFIELD>::from_mont(s);
         return s;
     }
@@ -108,7 +115,7 @@ template <int SFIELD> struct IpaScalars {
         }
         return acc;
     }
-    ACC_D fe_t canonical(uint32_t i) const { return Fp<SFIELD>::from_mont(coeff_mont(i)); }
+    ACC_D fe_t canonical(uint32_t, uint32_t i) const { return Fp<SFIELD>::from_mont(coeff_mont(i)); }
 };
 
 // bits [pos, pos + c) of a 256-bit little-endian integer, c <= 24
@@ -127,9 +134,12 @@ template <class Src>
 __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint8_t *__restrict__ base_is_identity,
                                                  uint32_t *__restrict__ digits, uint32_t *__restrict__ hist) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t job = blockIdx.y;
     if (i >= sh.n) return;
-    fe_t s = src.canonical(i);
-    if (base_is_identity && base_is_identity[i]) s = Fp<0>::zero();   // identity bases contribute nothing
+    fe_t s = src.canonical(job, i);
+    if (base_is_identity && base_is_identity[sh.job_off[job] + i]) s = Fp<0>::zero();   // identity bases contribute nothing
+    digits += (size_t)job * sh.nwin * sh.n;
+    hist += (size_t)job * sh.sets_per_job * sh.nb;
     const uint32_t half = 1u << (sh.c - 1);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < sh.nwin; w++) {
@@ -237,13 +247,17 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict_
 __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__restrict__ digits,
                                                   uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t job = blockIdx.y;
     if (i >= sh.n) return;
+    digits += (size_t)job * sh.nwin * sh.n;
+    cursor += (size_t)job * sh.sets_per_job * sh.nb;
+    const uint32_t base_index = sh.job_off[job] + i;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t enc = digits[(size_t)w * sh.n + i];
         uint32_t mag = enc & 0x7fffffffu;
         if (mag) {
             uint32_t pos = atomicAdd(&cursor[w * sh.hist_stride + mag - 1], 1u);
-            entries[pos] = (w * sh.ent_stride + sh.ent_offset + i) | (enc & 0x80000000u);
+            entries[pos] = (w * sh.ent_stride + base_index) | (enc & 0x80000000u);
         }
     }
 }
@@ -473,28 +487,30 @@ __global__ void __launch_bounds__(128) k_reduce1(const xyzz_t *__restrict__ sum_
     }
 }
 
-// k_finish: out = sum_w 2^(c w) S_w (+ optional extra partials), then either the raw XYZZ partial
-// (multi-GPU: partials are gathered and combined later) or the normalised affine image.
+// k_finish (one CTA per job): out = sum_w 2^(c w) S_w (+ optional extra partials), then either the raw XYZZ
+// partial (multi-GPU: partials are gathered and combined later) or the normalised affine image.
 template <int CURVE>
 __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, uint32_t c,
                          const xyzz_t *__restrict__ extra, uint32_t n_extra, int normalise,
                          xyzz_t *__restrict__ out_partial, affine_t *__restrict__ out_affine,
                          uint32_t *__restrict__ out_inf) {
     using Cv = Curve<CURVE>;
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (threadIdx.x != 0) return;
+    const uint32_t job = blockIdx.x;
+    window_sums += (size_t)job * nwin;
     xyzz_t acc = Cv::identity();
     for (int w = (int)nwin - 1; w >= 0; w--) {
         if (!Cv::is_identity(acc)) for (uint32_t b = 0; b < c; b++) acc = Cv::dbl(acc);
         xyzz_t s = load_xyzz(window_sums + w);
         Cv::add(acc, s);
     }
-    for (uint32_t i = 0; i < n_extra; i++) { xyzz_t s = load_xyzz(extra + i); Cv::add(acc, s); }
-    if (out_partial) store_xyzz(out_partial, acc);
+    for (uint32_t i = 0; i < n_extra; i++) { xyzz_t s = load_xyzz(extra + (size_t)job * n_extra + i); Cv::add(acc, s); }
+    if (out_partial) store_xyzz(out_partial + job, acc);
     if (normalise) {
         affine_t a; uint32_t inf;
         Cv::to_affine(acc, a, inf);
-        store_fe(&out_affine->x, a.x); store_fe(&out_affine->y, a.y);
-        *out_inf = inf;
+        store_fe(&out_affine[job].x, a.x); store_fe(&out_affine[job].y, a.y);
+        out_inf[job] = inf;
     }
 }
 

@@ -51,8 +51,8 @@ class ShardedMSM:
         else:
             xy = np.ascontiguousarray(bases_slice, dtype=np.uint64).reshape(-1, 8)
             have = xy.shape[0]
-            self.bases = ctx.register_bases(curve, xy) if have == self.count else None
-        if have != self.count:
+            self.bases = ctx.register_bases(curve, xy) if have == self.count else None   # a handle may hold spare bases
+        if have < self.count or (have != self.count and self.bases is None):
             raise ValueError(f"rank {rank} owns {self.count} bases, got {have}")
         self.device = device or f"cuda:{torch.cuda.current_device()}"
         self.partial = torch.zeros(PARTIAL_WORDS, dtype=torch.int64, device=self.device)

@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=LOG_N_PER_GPU, help="log2 points per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-open", action="store_true", help="skip the IpaPC::open timing")
     ap.add_argument("--no-precompute", action="store_true", help="skip the per-key window table (one-shot bases)")
     ap.add_argument("--window-bits", type=int, default=0)
     args = ap.parse_args()
@@ -164,7 +165,7 @@ def main():
     start, count = shard_range(n_total, rank, world)
 
     # ---- inputs: key shard generated on its own GPU; scalars seeded per rank, pinned on the host
-    key = ctx.register_synthetic_bases(ab.PALLAS, SEED, count, first_index=start)
+    key = ctx.register_synthetic_bases(ab.PALLAS, SEED, count + 1, first_index=start)   # + 1: the hiding generator h
     if not args.no_precompute:       # commitment keys are registered once; the table is part of registration
         key.precompute(args.window_bits)
     elif args.window_bits:
@@ -253,6 +254,34 @@ def main():
                 assert ok
             decide[f"ipa_decide_tail_ms_2^{k}"] = round(statistics.median(ts), 4)
 
+    # ---- ipa-pc-as prove hot path: IpaPC::open on device (metric string: prove ms at degree 2^18), one GPU
+    if rank == 0 and world == 1 and not args.no_open:
+        import hashlib
+        from accumulation_b200.mirror import CommitterKey, InnerProductArgPC, _int_to_fe
+
+        def squeeze(prev, l, r):   # host transcript stand-in, 128-bit challenges (src/ipa_pc_as/mod.rs:42)
+            h = hashlib.blake2s(b"" if prev is None else prev.tobytes())
+            h.update(l[0].tobytes()); h.update(r[0].tobytes())
+            return _int_to_fe(1, int.from_bytes(h.digest()[:16], "little") | 1)
+
+        for k in (18, 20):
+            if (1 << k) > count - 1:
+                continue
+            n = 1 << k
+            ck = CommitterKey(key, n)
+            coeffs = rand_scalars(n, SEED + 99)
+            hp = ctx.download_bases(key, n, 1).reshape(8)
+            z = rand_scalars(1, SEED + 98).reshape(4)
+            ts = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                l_vec, r_vec, fk, c, chs = InnerProductArgPC.open(ck, coeffs, z, hp, squeeze, log_d=k)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ok, _, _ = ctx.ipa_check_final_key(key, np.array(chs), fk, 0)     # the proof's final key passes the decider
+            assert ok
+            decide[f"ipa_open_ms_2^{k}"] = round(min(ts), 3)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -264,7 +293,7 @@ def main():
     verified = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cref   # checker + reported baseline only
-        pts = ctx.download_bases(key)
+        pts = ctx.download_bases(key, 0, count)
         t0 = time.perf_counter()
         exp = cref.msm_ark(0, pts, sc_np)
         dt = time.perf_counter() - t0

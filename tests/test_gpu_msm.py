@@ -127,14 +127,23 @@ def test_commit_with_randomizer(ctx, keys, curve):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-def test_msm_batch(ctx, keys, curve):
-    pts, B = keys[curve]
+@pytest.mark.parametrize("n,k,precompute", [(2048, 3, False), (300, 10, False), (6000, 8, True), (1, 2, False)])
+def test_msm_batch(ctx, curve, n, k, precompute):
+    """k scalar vectors over one key in shared passes of the pipeline (hp_as::decide: 3, NARK prove: 3-8);
+    includes an all-zero vector (identity result) and a constant vector among the jobs."""
     sf = cref.scalar_field(curve)
-    n, k = 2048, 3
-    sc = cref.gen_scalars(sf, 40, n * k, True).reshape(k, n, 4)
-    xy, inf = ctx.msm_batch(B, sc)
+    pts = cref.gen_points(curve, 140 + curve, max(n, 1) + 5)
+    B = ctx.register_bases(curve, pts)
+    if precompute:
+        B.precompute(12)
+    sc = cref.gen_scalars(sf, 40 + n, n * k, True).reshape(k, n, 4)
+    sc[1] = 0
+    if k > 2:
+        sc[2] = sc[2][0]
+    xy, inf = ctx.msm_batch(B, sc, offset=3)
     for j in range(k):
-        assert same_point((xy[j], inf[j]), cref.commit(curve, pts[:n], sc[j]))
+        assert same_point((xy[j], inf[j]), cref.commit(curve, pts[3:3 + n], sc[j])), j
+    B.release()
 
 
 @pytest.mark.parametrize("c", [4, 7, 8, 11, 13, 15, 16])
