@@ -189,6 +189,19 @@ class Context:
                                                     _p(_u64(point_mont)), _p(_u64(h_prime_xy)), C.byref(sess)), "ipa_open_begin")
         return int(sess.value)
 
+    def ipa_open_begin_combined(self, bases: "Bases", challenges_mont, alphas_mont, point_mont, h_prime_xy, random_poly_mont=None):
+        """-> (session, P(point)) with P = [random poly] + sum_j alpha_j h_j(X) built on the device"""
+        ch = _u64(challenges_mont)
+        m, k = ch.shape[0], ch.shape[1]
+        rp = None if random_poly_mont is None else _u64(random_poly_mont).reshape(-1, 4)
+        sess = C.c_uint64(0)
+        ev = np.empty(4, dtype=np.uint64)
+        self._check(self._lib.accmsm_ipa_open_begin_combined(self._h, C.c_uint64(bases.handle), _p(ch), C.c_int(m), C.c_int(k),
+                                                             _p(_u64(alphas_mont)), _p(rp), C.c_size_t(0 if rp is None else rp.shape[0]),
+                                                             _p(_u64(point_mont)), _p(_u64(h_prime_xy)), C.byref(sess), _p(ev)),
+                    "ipa_open_begin_combined")
+        return int(sess.value), ev
+
     def ipa_open_round(self, session: int):
         l, r = np.empty(8, dtype=np.uint64), np.empty(8, dtype=np.uint64)
         li, ri = C.c_uint8(0), C.c_uint8(0)
@@ -204,6 +217,62 @@ class Context:
         fk, c = np.empty(8, dtype=np.uint64), np.empty(4, dtype=np.uint64)
         self._check(self._lib.accmsm_ipa_open_finish(self._h, C.c_uint64(session), _p(fk), _p(c)), "ipa_open_finish")
         return fk, c
+
+    # ---- fused steps
+    def hp_decide(self, bases: "Bases", a, b, expected_xy, expected_inf, hiding_index: int = 0, randomness=None):
+        a, b = _u64(a).reshape(-1, 4), _u64(b).reshape(-1, 4)
+        n = min(a.shape[0], b.shape[0])
+        exp = _u64(expected_xy).reshape(3, 8)
+        einf = np.ascontiguousarray(expected_inf, dtype=np.uint8).reshape(3)
+        r = None if randomness is None else _u64(randomness).reshape(3, 4)
+        out = np.empty((3, 8), dtype=np.uint64)
+        oinf = np.zeros(3, dtype=np.uint8)
+        acc = C.c_int(0)
+        self._check(self._lib.accmsm_hp_decide(self._h, C.c_uint64(bases.handle), _p(a), _p(b), C.c_size_t(n), C.c_size_t(hiding_index),
+                                               _p(r), _p(exp), _p(einf), C.byref(acc), _p(out), _p(oinf)), "hp_decide")
+        return bool(acc.value), out, oinf
+
+    def hp_product_poly_comm(self, bases: "Bases", a_vecs, b_vecs, mu, length: int, hiding_a=None, hiding_b=None, want_tvecs=False):
+        a_vecs = [_u64(v).reshape(-1, 4) for v in a_vecs]
+        b_vecs = [_u64(v).reshape(-1, 4) for v in b_vecs]
+        n = len(a_vecs)
+        al = np.array([v.shape[0] for v in a_vecs], dtype=np.uint64)
+        bl = np.array([v.shape[0] for v in b_vecs], dtype=np.uint64)
+        ha = None if hiding_a is None else _u64(hiding_a).reshape(-1, 4)
+        hb = None if hiding_b is None else _u64(hiding_b).reshape(-1, 4)
+        low, high = np.empty((max(n - 1, 0), 8), dtype=np.uint64), np.empty((max(n - 1, 0), 8), dtype=np.uint64)
+        linf, hinf = np.zeros(max(n - 1, 0), dtype=np.uint8), np.zeros(max(n - 1, 0), dtype=np.uint8)
+        tv = np.empty((2 * n - 1, length, 4), dtype=np.uint64) if want_tvecs else None
+        self._check(self._lib.accmsm_hp_product_poly_comm(self._h, C.c_uint64(bases.handle), self._ptrs(a_vecs), _p(al), self._ptrs(b_vecs),
+                                                          _p(bl), C.c_int(n), _p(_u64(mu)), C.c_size_t(length), _p(ha),
+                                                          C.c_size_t(0 if ha is None else ha.shape[0]), _p(hb),
+                                                          C.c_size_t(0 if hb is None else hb.shape[0]), _p(low), _p(linf), _p(high),
+                                                          _p(hinf), _p(tv)), "hp_product_poly_comm")
+        return (low, linf), (high, hinf), tv
+
+    def register_csr(self, field: int, mats) -> int:
+        rps = [np.ascontiguousarray(m[0], dtype=np.uint32) for m in mats]
+        cls = [np.ascontiguousarray(m[1], dtype=np.uint32) for m in mats]
+        cfs = [_u64(m[2]).reshape(-1, 4) for m in mats]
+        h = C.c_uint64(0)
+        self._check(self._lib.accmsm_register_csr(self._h, C.c_int(field), C.c_int(len(mats)), self._ptrs(rps), self._ptrs(cls),
+                                                  self._ptrs(cfs), C.c_size_t(rps[0].size - 1), C.byref(h)), "register_csr")
+        return int(h.value)
+
+    def release_csr(self, handle: int):
+        self._check(self._lib.accmsm_release_csr(self._h, C.c_uint64(handle)), "release_csr")
+
+    def csr_matvec_commit(self, bases: "Bases", csr: int, n_mats: int, n_rows: int, inp, wit, hiding_index: int = 0, blinders=None,
+                          want_vecs: bool = True):
+        inp, wit = _u64(inp).reshape(-1, 4), _u64(wit).reshape(-1, 4)
+        bl = None if blinders is None else _u64(blinders).reshape(n_mats, 4)
+        vecs = [np.empty((n_rows, 4), dtype=np.uint64) for _ in range(n_mats)] if want_vecs else None
+        out = np.empty((n_mats, 8), dtype=np.uint64)
+        oinf = np.zeros(n_mats, dtype=np.uint8)
+        self._check(self._lib.accmsm_csr_matvec_commit(self._h, C.c_uint64(bases.handle), C.c_uint64(csr), _p(inp), C.c_size_t(inp.shape[0]),
+                                                       _p(wit), C.c_size_t(wit.shape[0]), C.c_size_t(hiding_index), _p(bl),
+                                                       None if vecs is None else self._ptrs(vecs), _p(out), _p(oinf)), "csr_matvec_commit")
+        return vecs, out, oinf
 
     # ---- field-vector kernels
     def compute_coeffs(self, field: int, challenges_mont):
@@ -313,8 +382,8 @@ class Bases:
 
 
 from .mirror import (  # noqa: E402
-    ASForHadamardProducts, CommitterKey, InnerProductArgPC, PedersenCommitment, SuccinctCheckPolynomial, matrix_vec_mul,
+    ASForHadamardProducts, CommitterKey, InnerProductArgPC, PedersenCommitment, R1CSNark, SuccinctCheckPolynomial, matrix_vec_mul,
 )
 
 __all__ = ["Context", "Bases", "AccmsmError", "PALLAS", "VESTA", "FP", "FQ", "scalar_field", "PedersenCommitment",
-           "CommitterKey", "InnerProductArgPC", "SuccinctCheckPolynomial", "ASForHadamardProducts", "matrix_vec_mul"]
+           "CommitterKey", "InnerProductArgPC", "SuccinctCheckPolynomial", "ASForHadamardProducts", "R1CSNark", "matrix_vec_mul"]

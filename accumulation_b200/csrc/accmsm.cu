@@ -2,6 +2,7 @@
 // declared in include/accmsm.h.  No CPU arithmetic path exists here: every group / field operation is a
 // CUDA kernel from msm.cuh / vec.cuh, and every entry point fails with ACCMSM_E_CUDA without a device.
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -50,6 +51,8 @@ template <class T> struct DevBuf {
 
 struct IpaSession;
 void ipa_session_free(IpaSession *s);
+struct CsrSet;
+void csr_set_free(CsrSet *c);
 
 struct accmsm_ctx {
     int device = 0;
@@ -59,6 +62,9 @@ struct accmsm_ctx {
     std::string last_error;
     std::unordered_map<uint64_t, Bases> bases;
     std::unordered_map<uint64_t, struct IpaSession *> ipa_sessions;
+    std::vector<struct IpaSession *> ipa_free;
+    std::unordered_map<uint64_t, struct CsrSet *> csr_sets;
+    std::vector<std::pair<void *, size_t>> vec_cache;   // recycled scratch blocks of the field-vector entry points
     uint64_t next_handle = 1;
     int window_bits = 0;
     uint64_t launches = 0;
@@ -133,6 +139,7 @@ bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
 struct MsmJobs {
     uint32_t njobs = 1;
     size_t offset[MAX_JOBS] = {0};     // first base of every job inside the key
+    uint32_t tail_base = NONE_ID;      // index of the hiding generator when the last pair of every job is (H, r)
     MsmJobs() {}
     explicit MsmJobs(size_t off) { offset[0] = off; }
 };
@@ -141,6 +148,7 @@ MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, 
     MsmShape sh;
     sh.n = (uint32_t)n;
     sh.njobs = jobs.njobs;
+    sh.tail_base = jobs.tail_base;
     for (int j = 0; j < MAX_JOBS; j++) sh.job_off[j] = j < (int)jobs.njobs ? (uint32_t)jobs.offset[j] : 0u;
     if (use_table(ctx, B, n)) {
         sh.c = B.pre_c;
@@ -400,6 +408,9 @@ void accmsm_destroy(accmsm_ctx *ctx) {
         if (kv.second.d_table) cudaFree(kv.second.d_table);
     }
     for (auto &kv : ctx->ipa_sessions) ipa_session_free(kv.second);
+    for (auto *fs : ctx->ipa_free) ipa_session_free(fs);
+    for (auto &kv : ctx->csr_sets) csr_set_free(kv.second);
+    for (auto &b : ctx->vec_cache) cudaFree(b.first);
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release();
@@ -588,20 +599,18 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
     if (n > B->n || hiding_index >= B->n) return fail_arg(ctx, "commit: range exceeds registered bases");
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    // randomizer * hiding_generator as a one-point MSM whose XYZZ partial is folded into the main MSM's finish
-    CU(ctx, ctx->partial.ensure(1));
-    CU(ctx, ctx->scalars.ensure(std::max<size_t>(n, 1) * 32));
+    // one pass over n + 1 pairs: the elements against the generators, then (hiding generator, randomizer)
     clear_marks(ctx);
-    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, randomizer_mont, 32, cudaMemcpyHostToDevice, st));
-    int rc = msm_mem1(ctx, *B, hiding_index, 1, ctx->scalars.p, 1, nullptr, 0, ctx->partial.p, false, st);
+    CU(ctx, ctx->scalars.ensure((n + 1) * 32));
+    mark(ctx, ST_H2D, st);
+    if (n) CU(ctx, cudaMemcpyAsync(ctx->scalars.p, elems_mont, n * 32, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->scalars.p + n * 32, randomizer_mont, 32, cudaMemcpyHostToDevice, st));
+    MsmJobs jobs(0);
+    jobs.tail_base = (uint32_t)hiding_index;
+    const uint8_t *ptr = ctx->scalars.p;
+    int rc = msm_mem(ctx, *B, jobs, n + 1, &ptr, 1, nullptr, 0, nullptr, true, st);
     if (rc) return rc;
-    if (n == 0) {
-        if (B->curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, ctx->partial.p, 1, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
-        else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, ctx->partial.p, 1, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
-        ctx->launches++;
-        return fetch_affine(ctx, out_xy, out_inf, st);
-    }
-    return msm_host_scalars(ctx, *B, 0, n, elems_mont, 1, ctx->partial.p, 1, out_xy, out_inf);
+    return fetch_affine(ctx, out_xy, out_inf, st);
 }
 
 int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
@@ -719,3 +728,4 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
 
 #include "vec_api.inc"
 #include "ipa_api.inc"
+#include "fused_api.inc"

@@ -47,6 +47,10 @@ struct MsmShape {
     uint32_t njobs;
     uint32_t sets_per_job;   // nwin (plain key) or 1 (window table)
     uint32_t job_off[MAX_JOBS];
+    // Optional hiding term: when tail_base != NONE_ID the last of the n pairs of every job is
+    // (base tail_base, randomizer) -- PedersenCommitment::commit(ck, elems, Some(r)) = MSM + r * hiding_generator
+    // in the same pass.
+    uint32_t tail_base;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -137,7 +141,8 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
     const uint32_t job = blockIdx.y;
     if (i >= sh.n) return;
     fe_t s = src.canonical(job, i);
-    if (base_is_identity && base_is_identity[sh.job_off[job] + i]) s = Fp<0>::zero();   // identity bases contribute nothing
+    const uint32_t base_index = (sh.tail_base != NONE_ID && i == sh.n - 1) ? sh.tail_base : sh.job_off[job] + i;
+    if (base_is_identity && base_is_identity[base_index]) s = Fp<0>::zero();   // identity bases contribute nothing
     digits += (size_t)job * sh.nwin * sh.n;
     hist += (size_t)job * sh.sets_per_job * sh.nb;
     const uint32_t half = 1u << (sh.c - 1);
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__
     if (i >= sh.n) return;
     digits += (size_t)job * sh.nwin * sh.n;
     cursor += (size_t)job * sh.sets_per_job * sh.nb;
-    const uint32_t base_index = sh.job_off[job] + i;
+    const uint32_t base_index = (sh.tail_base != NONE_ID && i == sh.n - 1) ? sh.tail_base : sh.job_off[job] + i;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t enc = digits[(size_t)w * sh.n + i];
         uint32_t mag = enc & 0x7fffffffu;

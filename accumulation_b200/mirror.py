@@ -154,20 +154,44 @@ class ASForHadamardProducts:
         return low, high
 
     @staticmethod
+    def compute_t_vecs_and_product_poly_comm(ck: CommitterKey, a_vecs, b_vecs, mu_challenges, hp_vec_len, hiding_vecs=None):
+        """compute_t_vecs (:288-349) feeding compute_product_poly_comm (:354-388) without the t-vectors leaving HBM.
+        -> (low, high) lists of (xy, inf)"""
+        ha, hb = hiding_vecs if hiding_vecs is not None else (None, None)
+        (low, linf), (high, hinf), _ = ck.bases.ctx.hp_product_poly_comm(ck.bases, a_vecs, b_vecs, mu_challenges, hp_vec_len, ha, hb)
+        return [(low[i], int(linf[i])) for i in range(low.shape[0])], [(high[i], int(hinf[i])) for i in range(high.shape[0])]
+
+    @staticmethod
     def decide(ck: CommitterKey, instance, witness) -> bool:        # :894-925
         """instance = (comm_1, comm_2, comm_3) as (xy, inf) pairs; witness = (a_vec, b_vec, randomness|None),
-        randomness = (rand_1, rand_2, rand_3)."""
-        from . import scalar_field
-        ctx = ck.bases.ctx
+        randomness = (rand_1, rand_2, rand_3).  One fused device call: Hadamard product + the three commitments in a
+        shared pass of the MSM pipeline + the comparison."""
         a_vec, b_vec, rand = witness
-        field = scalar_field(ck.curve)
-        product = ASForHadamardProducts.compute_hp(ctx, field, a_vec, b_vec)
-        r = rand if rand is not None else (None, None, None)
-        tests = [PedersenCommitment.commit(ck, a_vec, r[0]), PedersenCommitment.commit(ck, b_vec, r[1]),
-                 PedersenCommitment.commit(ck, product, r[2])]
-        for (got_xy, got_inf), (exp_xy, exp_inf) in zip(tests, instance):
-            if got_inf != int(exp_inf):
-                return False
-            if not got_inf and not np.array_equal(got_xy, np.asarray(exp_xy, dtype=np.uint64)):
-                return False
-        return True
+        a = np.ascontiguousarray(a_vec, dtype=np.uint64).reshape(-1, 4)[: ck.num_generators]
+        b = np.ascontiguousarray(b_vec, dtype=np.uint64).reshape(-1, 4)[: ck.num_generators]
+        exp_xy = np.array([np.asarray(c[0], dtype=np.uint64) for c in instance])
+        exp_inf = np.array([int(c[1]) for c in instance], dtype=np.uint8)
+        r = None if rand is None else np.array([np.asarray(x, dtype=np.uint64) for x in rand])
+        ok, _, _ = ck.bases.ctx.hp_decide(ck.bases, a, b, exp_xy, exp_inf, hiding_index=ck.num_generators, randomness=r)
+        return ok
+
+
+class R1CSNark:
+    """The mat-vec + commitment steps of src/r1cs_nark_as/r1cs_nark/mod.rs (prove :183-218, verify :356-389) and of
+    ASForR1CSNark::decide (src/r1cs_nark_as/mod.rs:1052-1097) with the index matrices registered once."""
+
+    def __init__(self, ck: CommitterKey, matrices):
+        from . import scalar_field
+        self.ck = ck
+        self.n_mats = len(matrices)
+        self.n_rows = int(np.asarray(matrices[0][0]).size - 1)
+        self.csr = ck.bases.ctx.register_csr(scalar_field(ck.curve), matrices)
+
+    def matvec_commit(self, inp, wit, blinders=None):
+        """-> ([M (input || witness)], [(comm_xy, inf)])"""
+        vecs, xy, inf = self.ck.bases.ctx.csr_matvec_commit(self.ck.bases, self.csr, self.n_mats, self.n_rows, inp, wit,
+                                                             hiding_index=self.ck.num_generators, blinders=blinders)
+        return vecs, [(xy[i], int(inf[i])) for i in range(self.n_mats)]
+
+    def release(self):
+        self.ck.bases.ctx.release_csr(self.csr)

@@ -139,6 +139,13 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
  * (probability ~2^-255 for sponge challenges) is not representable and is not detected. */
 int accmsm_ipa_open_begin(accmsm_ctx *ctx, uint64_t handle, const uint64_t *coeffs_mont, size_t n_coeffs, int k,
                           const uint64_t point_mont[4], const uint64_t h_prime_xy[8], uint64_t *session);
+/* Same session, but the polynomial being opened is built on the device: AtomicASForInnerProductArgPC::prove opens
+ * the combined succinct-check polynomial P = [random linear poly] + sum_j alpha_j h_j(X) (src/ipa_pc_as/mod.rs:391-404)
+ * at the new challenge point; eval_out receives P(point) (:439).  challenges: m x k x 4, xi_1 first. */
+int accmsm_ipa_open_begin_combined(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int m, int k,
+                                   const uint64_t *alphas_mont, const uint64_t *random_poly_mont, size_t n_random,
+                                   const uint64_t point_mont[4], const uint64_t h_prime_xy[8], uint64_t *session,
+                                   uint64_t eval_out[4]);
 int accmsm_ipa_open_round(accmsm_ctx *ctx, uint64_t session, uint64_t l_xy[8], uint8_t *l_inf,
                           uint64_t r_xy[8], uint8_t *r_inf);
 int accmsm_ipa_open_fold(accmsm_ctx *ctx, uint64_t session, const uint64_t xi_mont[4], const uint64_t xi_inv_mont[4]);
@@ -176,6 +183,31 @@ int accmsm_csr_matvec(accmsm_ctx *ctx, int field, int n_mats, const uint32_t *co
                       const uint32_t *const *cols, const uint64_t *const *coeffs_mont, size_t n_rows,
                       const uint64_t *input, size_t n_input, const uint64_t *witness, size_t n_witness,
                       uint64_t *const *out);
+
+/* ---- fused steps: vector kernel -> commitments without the vectors leaving HBM ---------- */
+/* ASForHadamardProducts::decide (src/hp_as/mod.rs:894-925): product = a o b; accept iff Commit(a, r1) == comm_1 &&
+ * Commit(b, r2) == comm_2 && Commit(product, r3) == comm_3.  The three commitments share one pass of the MSM
+ * pipeline.  randomness_mont: 3 x 4 or NULL (no zk); hiding_index: position of the hiding generator in the key. */
+int accmsm_hp_decide(accmsm_ctx *ctx, uint64_t handle, const uint64_t *a_mont, const uint64_t *b_mont, size_t n,
+                     size_t hiding_index, const uint64_t *randomness_mont, const uint64_t *expected_xy,
+                     const uint8_t *expected_inf, int *accept, uint64_t *out_xy, uint8_t *out_inf);
+/* compute_t_vecs + compute_product_poly_comm (src/hp_as/mod.rs:288-388): all t-vectors except the middle one are
+ * committed (no randomiser).  out_low / out_high: (n_in - 1) x 8; out_tvecs (nullable): (2 n_in - 1) x len x 4. */
+int accmsm_hp_product_poly_comm(accmsm_ctx *ctx, uint64_t handle, const uint64_t *const *a_vecs, const size_t *a_lens,
+                                const uint64_t *const *b_vecs, const size_t *b_lens, int n_in, const uint64_t *mu,
+                                size_t len, const uint64_t *hiding_a, size_t n_ha, const uint64_t *hiding_b, size_t n_hb,
+                                uint64_t *out_low_xy, uint8_t *out_low_inf, uint64_t *out_high_xy, uint8_t *out_high_inf,
+                                uint64_t *out_tvecs);
+/* R1CS matrices registered once (fixed from index time on: src/r1cs_nark_as/r1cs_nark/mod.rs:78-124); then
+ * t_M = M (input || witness) and comm_M = Commit(t_M, blinder_M) for all matrices in one call
+ * (prover :183-185 + :216-218, verifier :356-361 + :375-389, AS decider src/r1cs_nark_as/mod.rs:1052-1097).
+ * out_vecs: NULL or n_mats pointers (each nullable) receiving t_M; blinders_mont: n_mats x 4 or NULL. */
+int accmsm_register_csr(accmsm_ctx *ctx, int field, int n_mats, const uint32_t *const *row_ptr, const uint32_t *const *cols,
+                        const uint64_t *const *coeffs_mont, size_t n_rows, uint64_t *handle);
+int accmsm_release_csr(accmsm_ctx *ctx, uint64_t handle);
+int accmsm_csr_matvec_commit(accmsm_ctx *ctx, uint64_t key_handle, uint64_t csr_handle, const uint64_t *input, size_t n_input,
+                             const uint64_t *witness, size_t n_witness, size_t hiding_index, const uint64_t *blinders_mont,
+                             uint64_t *const *out_vecs, uint64_t *out_xy, uint8_t *out_inf);
 
 #ifdef __cplusplus
 }
