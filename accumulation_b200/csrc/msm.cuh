@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
     digits += (size_t)job * sh.nwin * sh.n;
     hist += (size_t)job * sh.sets_per_job * sh.nb;
     const uint32_t half = 1u << (sh.c - 1);
+    const unsigned am = __activemask();            // lanes with i < n (the others have returned)
+    const uint32_t lane = threadIdx.x & 31, leader = __ffs(am) - 1;
     uint32_t carry = 0;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t raw = extract_bits(s.l, w * sh.c, sh.c) + carry;
@@ -160,7 +162,16 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
         }
         digits[(size_t)w * sh.n + i] = enc;
         uint32_t mag = enc & 0x7fffffffu;
-        if (mag) atomicAdd(&hist[w * sh.hist_stride + mag - 1], 1u);
+        // Histogram update.  When every lane of the warp lands in the same bucket (constant scalar vectors: the
+        // reference's own fixtures, src/hp_as/mod.rs:991) one lane adds the warp's count instead of 32 lanes
+        // serialising on one L2 address.
+        const uint32_t key = mag ? w * sh.hist_stride + mag - 1 : NONE_ID;
+        const uint32_t key0 = __shfl_sync(am, key, leader);
+        if (__all_sync(am, key == key0)) {
+            if (mag && lane == leader) atomicAdd(&hist[key], (uint32_t)__popc(am));
+        } else if (mag) {
+            atomicAdd(&hist[key], 1u);
+        }
     }
 }
 
@@ -257,13 +268,22 @@ __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__
     digits += (size_t)job * sh.nwin * sh.n;
     cursor += (size_t)job * sh.sets_per_job * sh.nb;
     const uint32_t base_index = (sh.tail_base != NONE_ID && i == sh.n - 1) ? sh.tail_base : sh.job_off[job] + i;
+    const unsigned am = __activemask();
+    const uint32_t lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+    const uint32_t rank = __popc(am & ((1u << lane) - 1u));
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t enc = digits[(size_t)w * sh.n + i];
         uint32_t mag = enc & 0x7fffffffu;
-        if (mag) {
-            uint32_t pos = atomicAdd(&cursor[w * sh.hist_stride + mag - 1], 1u);
-            entries[pos] = (w * sh.ent_stride + base_index) | (enc & 0x80000000u);
+        const uint32_t key = mag ? w * sh.hist_stride + mag - 1 : NONE_ID;
+        const uint32_t key0 = __shfl_sync(am, key, leader);
+        uint32_t pos = 0;
+        if (__all_sync(am, key == key0)) {          // warp-uniform bucket: one atomic reserves the warp's range
+            if (mag && lane == leader) pos = atomicAdd(&cursor[key], (uint32_t)__popc(am));
+            pos = __shfl_sync(am, pos, leader) + rank;
+        } else if (mag) {
+            pos = atomicAdd(&cursor[key], 1u);
         }
+        if (mag) entries[pos] = (w * sh.ent_stride + base_index) | (enc & 0x80000000u);
     }
 }
 
@@ -348,7 +368,15 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
                 if (first_run) { slot_pt[2 * threadIdx.x] = acc; head_id = k; first_run = false; }
                 else store_xyzz(buckets + k, acc);  // a run strictly inside this slice is complete
                 acc = Cv::identity();
-                do { k++; bend = offsets[k + 1]; } while (bend == p);
+                k++; bend = offsets[k + 1];
+                if (bend == p) {                   // empty buckets ahead: binary search for the bucket holding entry p
+                    uint32_t blo = k + 1, bhi = nkeys - 1;   // (a linear walk over 2^19 empty buckets is what makes
+                    while (blo < bhi) {                      //  constant scalar vectors slow otherwise)
+                        uint32_t mid = (blo + bhi) >> 1;
+                        if (offsets[mid + 1] > p) bhi = mid; else blo = mid + 1;
+                    }
+                    k = blo; bend = offsets[k + 1];
+                }
             }
             const uint32_t cur_sign = ent >> 31;
             affine_t cur = pt;
