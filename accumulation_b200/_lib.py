@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libaccmsm.so")
+SO_PATH = os.environ.get("ACCMSM_SO") or os.path.join(HERE, "libaccmsm.so")   # ACCMSM_SO: development builds (tuning sweeps)
 
 # every symbol include/accmsm.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [

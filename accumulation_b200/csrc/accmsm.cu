@@ -136,6 +136,10 @@ bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
     return n >= (size_t(1) << (B.pre_c > 4 ? B.pre_c - 4 : 0));
 }
 
+#ifndef RED_L0_BLK
+#define RED_L0_BLK 32     // threads per row / column sum of the first reduction level (one warp: 16-32 serial adds + 5 shuffle steps; measured best of 32/64/128/256)
+#endif
+
 struct MsmJobs {
     uint32_t njobs = 1;
     size_t offset[MAX_JOBS] = {0};     // first base of every job inside the key
@@ -240,31 +244,46 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
     mark(ctx, ST_REDUCE, st);
     const xyzz_t *window_sums = nullptr;
     {
-        uint32_t seg = std::min<uint32_t>(RED0_SEG, sh.nb);
-        uint32_t per_set = sh.nb / seg;
-        uint32_t items = per_set * nsets;
-        CU(ctx, ctx->red_sum[0].ensure(items));
-        CU(ctx, ctx->red_wsum[0].ensure(items));
-        CU(ctx, ctx->red_sum[1].ensure(items / 32 + nsets));
-        CU(ctx, ctx->red_wsum[1].ensure(items / 32 + nsets));
-        k_reduce0<CURVE><<<(items + 127) / 128, 128, 0, st>>>(ctx->offsets.p, ctx->buckets.p, sh.nb, seg, items,
-                                                              ctx->red_sum[0].p, ctx->red_wsum[0].p);
-        ctx->launches++;
-        uint32_t log2_span = 0;
-        while ((1u << log2_span) < seg) log2_span++;
-        int cur = 0;
-        while (per_set > 1) {
-            uint32_t per_out = (per_set + 31) / 32;
-            uint32_t warps = per_out * nsets;
-            k_reduce1<CURVE><<<(warps * 32 + 127) / 128, 128, 0, st>>>(ctx->red_sum[cur].p, ctx->red_wsum[cur].p, per_set,
-                                                                       per_out, nsets, log2_span,
-                                                                       ctx->red_sum[cur ^ 1].p, ctx->red_wsum[cur ^ 1].p);
+        // depth-optimised reduction (msm.cuh): rows / columns of the bucket index, twice, then 32-item weighted sums
+        const uint32_t m = sh.c - 1, N0 = sh.nb;
+        const uint32_t C0 = N0 > 1024 ? 1u << (m / 2) : 0, R0 = N0 > 1024 ? N0 / C0 : 0;
+        CU(ctx, ctx->red_sum[0].ensure((size_t)nsets * (R0 + C0) + 1));
+        CU(ctx, ctx->red_wsum[0].ensure((size_t)nsets * 128));
+        CU(ctx, ctx->red_wsum[1].ensure(nsets));
+        xyzz_t *scratch = ctx->red_sum[0].p, *leaf = ctx->red_wsum[0].p, *sums = ctx->red_wsum[1].p;
+        CU(ctx, cudaMemsetAsync(leaf, 0, (size_t)nsets * 128 * sizeof(xyzz_t), st));   // all-zero = identity (ZZ == 0)
+        int nlevels;
+        SumTasks t1; memset(&t1, 0, sizeof t1);
+        if (N0 > 1024) {
+            SumTasks t0; memset(&t0, 0, sizeof t0);
+            t0.ntasks = 2;
+            t0.t[0] = SumTask{0, 0, R0, C0, C0, 1};          // R_hi = sum_lo B[hi][lo]
+            t0.t[1] = SumTask{0, R0, C0, R0, 1, C0};         // C_lo = sum_hi B[hi][lo]
+            k_sums<CURVE, RED_L0_BLK><<<dim3(R0 + C0, nsets), RED_L0_BLK, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, scratch, R0 + C0, t0);
+            t1.ntasks = 4;
+            t1.t[0] = SumTask{0, 0, R0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, R0 / 32, 1, 32};
+            t1.t[2] = SumTask{R0, 64, C0 / 32, 32, 32, 1};   t1.t[3] = SumTask{R0, 96, 32, C0 / 32, 1, 32};
+            k_sums<CURVE, 32><<<dim3(R0 / 32 + C0 / 32 + 64, nsets), 32, 0, st>>>(scratch, R0 + C0, nullptr, leaf, 128, t1);
+            ctx->launches += 2;
+            nlevels = 2;
+        } else if (N0 > 32) {
+            t1.ntasks = 2;
+            t1.t[0] = SumTask{0, 0, N0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, N0 / 32, 1, 32};
+            k_sums<CURVE, 32><<<dim3(N0 / 32 + 32, nsets), 32, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
             ctx->launches++;
-            log2_span += 5;
-            per_set = per_out;
-            cur ^= 1;
+            nlevels = 1;
+        } else {
+            t1.ntasks = 1;
+            t1.t[0] = SumTask{0, 0, N0, 1, 1, 1};
+            k_sums<CURVE, 32><<<dim3(N0, nsets), 32, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
+            ctx->launches++;
+            nlevels = 0;
         }
-        window_sums = ctx->red_wsum[cur].p;
+        uint32_t s0 = 0;
+        while (C0 && (1u << s0) < C0) s0++;
+        k_wsum_leaf<CURVE><<<nsets, 128, 0, st>>>(leaf, 128, nlevels, s0, sums);
+        ctx->launches++;
+        window_sums = sums;
     }
     mark(ctx, ST_FINISH, st);
     k_finish<CURVE><<<sh.njobs, 32, 0, st>>>(window_sums, sh.sets_per_job, sh.c, d_extra, n_extra, normalise ? 1 : 0,
@@ -486,8 +505,8 @@ int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, u
 }
 
 int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
-    if (!ctx || window_bits < 0 || (window_bits && (window_bits < 8 || window_bits > 22)))
-        return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 8..22");
+    if (!ctx || window_bits < 0 || (window_bits && (window_bits < 8 || window_bits > 21)))
+        return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 8..21");
     std::lock_guard<std::mutex> lock(ctx->mu);
     auto it = ctx->bases.find(handle);
     if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }

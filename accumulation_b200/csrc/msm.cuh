@@ -12,8 +12,8 @@
 //                 boundaries are merged by a segmented scan in shared memory (hot buckets are
 //                 tree-reduced, never serialised: constant scalar vectors cost the same as random ones)
 //   k_fixup       merges the two boundary partials of every CTA
-//   k_reduce0/1   bucket reduction sum_b b*B_b: thread-serial running sums over 16 buckets, then
-//                 warp-parallel suffix scans over 32 items per level
+//   k_sums /      bucket reduction sum_b b*B_b organised for depth: row / column sums of the bucket index (twice),
+//   k_wsum_leaf   then four 32-item weighted sums, one warp each
 //   k_finish      Horner combine of the window sums (c doublings per window), optional normalisation
 #pragma once
 #include <cuda_runtime.h>
@@ -25,7 +25,6 @@ constexpr uint32_t NONE_ID = 0xffffffffu;
 constexpr int ACC_THREADS = 256;       // threads per accumulate CTA
 constexpr int FIX_THREADS = 512;       // k_fixup: one CTA, FIX_PER_T slots per thread (<= 1536 slots fit in 227 KB)
 constexpr int FIX_PER_T = 3;
-constexpr int RED0_SEG = 16;           // buckets per thread in the first reduction level
 constexpr int MAX_WINDOWS = 64;
 constexpr int MAX_JOBS = 8;            // MSMs that share one pass of the pipeline (same key, same length)
 
@@ -449,28 +448,17 @@ __global__ void __launch_bounds__(FIX_THREADS) k_fixup(const uint32_t *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// bucket reduction  S_w = sum_{b=1..nb} b * B_{w,b}
+// bucket reduction  S = sum_{k < nb} (k + 1) * B_k  per bucket set, as  W + T  with  W = sum k B_k,  T = sum B_k.
+//
+// The tail of the MSM is bound by the latency of dependent point additions (one warp needs ~10k cycles per XYZZ
+// add, tools/latbench.cu), so the reduction is organised for depth, not for work: the bucket index is split
+// k = hi * C + lo and
+//     W = C * sum_hi hi * R_hi + sum_lo lo * C_lo,      R_hi = sum_lo B[hi][lo],   C_lo = sum_hi B[hi][lo]
+// turns one weighted sum over R * C items into plain (tree) sums plus two weighted sums over R and C items.
+// Applied twice (nb <= 2^20 -> <= 1024 -> <= 32) the weighted sums left are over <= 32 items: one warp each.
+// k_sums does every plain-sum level (tasks describe rows / columns), k_wsum_leaf the four 32-item weighted sums and
+// the recombination.  Depth for 2^19 buckets: ~12 + 5 + 10 additions + 15 doublings, instead of ~90.
 // ------------------------------------------------------------------------------------------------
-// level 0: one thread per RED0_SEG consecutive buckets: sum = sum_j B_j, wsum = sum_j (j + 1) B_j.
-template <int CURVE>
-__global__ void __launch_bounds__(128) k_reduce0(const uint32_t *__restrict__ offsets, const xyzz_t *__restrict__ buckets,
-                                                  uint32_t nb, uint32_t seg, uint32_t nitems_total,
-                                                  xyzz_t *__restrict__ sum_out, xyzz_t *__restrict__ wsum_out) {
-    using Cv = Curve<CURVE>;
-    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= nitems_total) return;
-    const uint32_t per_set = nb / seg;
-    const uint32_t set = it / per_set, base = (it % per_set) * seg;
-    xyzz_t run = Cv::identity(), acc = Cv::identity();
-    for (int j = (int)seg - 1; j >= 0; j--) {
-        uint32_t k = set * nb + base + j;
-        if (offsets[k + 1] != offsets[k]) { xyzz_t b = load_xyzz(buckets + k); Cv::add(run, b); }
-        Cv::add(acc, run);
-    }
-    store_xyzz(sum_out + it, run);
-    store_xyzz(wsum_out + it, acc);
-}
-
 ACC_D xyzz_t shfl_down_xyzz(const xyzz_t &p, int d) {
     xyzz_t r;
 #pragma unroll
@@ -483,40 +471,112 @@ ACC_D xyzz_t shfl_down_xyzz(const xyzz_t &p, int d) {
     return r;
 }
 
-// level >= 1: one warp per group of 32 consecutive items of a set, each item spanning `span` buckets:
-//   Sum = sum_j sum_j,  Wsum = sum_j wsum_j + span * sum_j j * sum_j
-// sum_j j*sum_j = sum_{j>=1} (suffix sum from j), by a Kogge-Stone suffix scan + warp reduction.
-template <int CURVE>
-__global__ void __launch_bounds__(128) k_reduce1(const xyzz_t *__restrict__ sum_in, const xyzz_t *__restrict__ wsum_in,
-                                                  uint32_t per_set_in, uint32_t per_set_out, uint32_t nsets,
-                                                  uint32_t log2_span, xyzz_t *__restrict__ sum_out,
-                                                  xyzz_t *__restrict__ wsum_out) {
+struct SumTask {
+    uint32_t in_off;      // first item of the task inside the set's input array
+    uint32_t out_off;     // first output inside the set's output array
+    uint32_t n_out;       // outputs
+    uint32_t len;         // items per output
+    uint32_t stride_out;  // input step between consecutive outputs
+    uint32_t stride_len;  // input step between consecutive items of one output
+};
+struct SumTasks {
+    SumTask t[4];
+    uint32_t ntasks;
+};
+
+// out[set][task.out_off + o] = sum_{j < len} in[set][task.in_off + o * stride_out + j * stride_len]
+// One CTA of BLK threads per output.  offsets != nullptr: `in` are buckets and empty ones (never written) are skipped.
+template <int CURVE, int BLK>
+__global__ void __launch_bounds__(BLK) k_sums(const xyzz_t *__restrict__ in, uint32_t in_set_stride,
+                                              const uint32_t *__restrict__ offsets, xyzz_t *__restrict__ out,
+                                              uint32_t out_set_stride, SumTasks tasks) {
     using Cv = Curve<CURVE>;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nsets * per_set_out) return;   // whole warp exits together
-    const uint32_t set = warp / per_set_out, grp = warp % per_set_out;
-    const uint32_t j = grp * 32 + lane;
-    const bool valid = j < per_set_in;
-    xyzz_t run = Cv::identity(), ws = Cv::identity();
-    if (valid) { run = load_xyzz(sum_in + set * per_set_in + j); ws = load_xyzz(wsum_in + set * per_set_in + j); }
-#pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {   // suffix scan: run_j = sum_{i >= j} sum_i
-        xyzz_t o = shfl_down_xyzz(run, d);
-        if (lane + d < 32) Cv::add(run, o);
+    __shared__ xyzz_t part[BLK / 32];
+    uint32_t o = blockIdx.x, ti = 0;
+    while (ti + 1 < tasks.ntasks && o >= tasks.t[ti].n_out) { o -= tasks.t[ti].n_out; ti++; }
+    const SumTask tk = tasks.t[ti];
+    const uint32_t set = blockIdx.y;
+    const xyzz_t *src = in + (size_t)set * in_set_stride;
+    const uint32_t *offs = offsets ? offsets + (size_t)set * in_set_stride : nullptr;
+    xyzz_t acc = Cv::identity();
+    for (uint32_t j = threadIdx.x; j < tk.len; j += BLK) {
+        uint32_t idx = tk.in_off + o * tk.stride_out + j * tk.stride_len;
+        if (!offs || offs[idx + 1] != offs[idx]) { xyzz_t b = load_xyzz(src + idx); Cv::add(acc, b); }
     }
-    xyzz_t tot = run;                     // lane 0 holds Sum
-    xyzz_t jr = lane >= 1 ? run : Cv::identity();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t live = tk.len < BLK ? tk.len : BLK;       // threads that may hold something
 #pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {   // reductions: sum_{j>=1} run_j  and  sum_j wsum_j
-        xyzz_t o = shfl_down_xyzz(jr, d);
-        xyzz_t o2 = shfl_down_xyzz(ws, d);
-        if (lane < d) { Cv::add(jr, o); Cv::add(ws, o2); }
+    for (int d = 16; d >= 1; d >>= 1) {
+        if ((uint32_t)d < live) {                            // uniform across the CTA
+            xyzz_t other = shfl_down_xyzz(acc, d);
+            if (lane < (uint32_t)d) Cv::add(acc, other);
+        }
     }
-    if (lane == 0) {
-        for (uint32_t b = 0; b < log2_span; b++) jr = Cv::dbl(jr);
-        Cv::add(ws, jr);
-        store_xyzz(sum_out + warp, tot);
-        store_xyzz(wsum_out + warp, ws);
+    if (BLK > 32) {
+        if (lane == 0) part[wid] = acc;
+        __syncthreads();
+        if (wid == 0) {
+            acc = lane < BLK / 32 && lane * 32 < live ? part[lane] : Cv::identity();
+#pragma unroll 1
+            for (int d = BLK / 64; d >= 1; d >>= 1) {
+                if ((uint32_t)d * 32 < live) {
+                    xyzz_t other = shfl_down_xyzz(acc, d);
+                    if (lane < (uint32_t)d) Cv::add(acc, other);
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * out_set_stride + tk.out_off + o, acc);
+}
+
+// Leaf of the reduction, one CTA of 4 warps per bucket set.  leaf[set][a][j], a < 4, j < 32: warp a computes
+// W_a = sum_j j * leaf[a][j] (suffix scan, then a sum over the lanes >= 1) and T_a = sum_j leaf[a][j]; then
+//   nlevels == 2:  S = 2^s0 * (2^5 * W_0 + W_1) + (2^5 * W_2 + W_3) + T_0
+//   nlevels == 1:  S = 2^5 * W_0 + W_1 + T_0            nlevels == 0:  S = W_0 + T_0
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_wsum_leaf(const xyzz_t *__restrict__ leaf, uint32_t leaf_set_stride, int nlevels,
+                                                    uint32_t s0, xyzz_t *__restrict__ out) {
+    using Cv = Curve<CURVE>;
+    __shared__ xyzz_t W[4];
+    __shared__ xyzz_t T0;
+    const uint32_t set = blockIdx.x, a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int narr = nlevels == 2 ? 4 : nlevels == 1 ? 2 : 1;
+    if ((int)a < narr) {
+        xyzz_t run = load_xyzz(leaf + (size_t)set * leaf_set_stride + a * 32 + lane);
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {            // suffix scan: run_j = sum_{i >= j} item_i
+            xyzz_t o = shfl_down_xyzz(run, d);
+            if (lane + d < 32) Cv::add(run, o);
+        }
+        if (a == 0 && lane == 0) T0 = run;
+        xyzz_t jr = lane >= 1 ? run : Cv::identity();   // sum_j j * item_j = sum_{j >= 1} run_j
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            xyzz_t o = shfl_down_xyzz(jr, d);
+            if (lane < (uint32_t)d) Cv::add(jr, o);
+        }
+        if (lane == 0) W[a] = jr;
+    }
+    __syncthreads();
+    // the two 2^5 recombinations run in parallel (threads 0 and 32), the outer one on thread 0
+    if (nlevels >= 1 && lane == 0 && (a == 0 || (a == 1 && nlevels == 2))) {
+        xyzz_t hi = W[2 * a];
+        for (int b = 0; b < 5; b++) hi = Cv::dbl(hi);
+        xyzz_t lo = W[2 * a + 1];
+        Cv::add(hi, lo);
+        W[2 * a] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        xyzz_t acc = W[0];
+        if (nlevels == 2) {
+            for (uint32_t b = 0; b < s0; b++) acc = Cv::dbl(acc);
+            xyzz_t lo = W[2];
+            Cv::add(acc, lo);
+        }
+        xyzz_t t = T0;
+        Cv::add(acc, t);
+        store_xyzz(out + set, acc);
     }
 }
 
