@@ -106,6 +106,17 @@ class Context:
                                          C.c_int(int(montgomery)), _p(out), C.byref(inf)), "msm")
         return out, int(inf.value)
 
+    def msm_oneshot(self, curve: int, bases_xy, scalars, montgomery: bool = True, infinity=None):
+        """VariableBaseMSM::multi_scalar_mul(&bases, &scalars).into_affine() for bases that are not a registered key"""
+        xy, sc = _u64(bases_xy).reshape(-1, 8), _u64(scalars).reshape(-1, 4)
+        n = min(xy.shape[0], sc.shape[0])                     # ark-ec truncates to the shorter slice
+        inf_in = None if infinity is None else np.ascontiguousarray(infinity, dtype=np.uint8)
+        out = np.empty(8, dtype=np.uint64)
+        inf = C.c_uint8(0)
+        self._check(self._lib.accmsm_msm_oneshot(self._h, C.c_int(curve), _p(xy), _p(inf_in), _p(sc), C.c_int(int(montgomery)),
+                                                 C.c_size_t(n), _p(out), C.byref(inf)), "msm_oneshot")
+        return out, int(inf.value)
+
     def msm_ptr(self, bases: "Bases", host_ptr: int, n: int, montgomery: bool = True, offset: int = 0):
         """Same as msm() for a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
         out = np.empty(8, dtype=np.uint64)

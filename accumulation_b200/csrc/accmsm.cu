@@ -74,6 +74,7 @@ struct accmsm_ctx {
     DevBuf<uint32_t> digits, hist, offsets, cursor, entries, cta_ids, tile_sums, tile_offs;
     DevBuf<xyzz_t> buckets, red_sum[2], red_wsum[2], cta_parts, partial;
     DevBuf<uint8_t> scalars, misc;
+    DevBuf<affine_t> oneshot_xy;
     affine_t *d_out_affine = nullptr;
     uint32_t *d_out_inf = nullptr;
     uint64_t *h_out = nullptr;   // pinned: 8 u64 affine + 1 u64 inf + 16 u64 partial
@@ -432,7 +433,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     for (auto &b : ctx->vec_cache) cudaFree(b.first);
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
-    ctx->scalars.release(); ctx->misc.release();
+    ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release();
     for (int i = 0; i < 2; i++) { ctx->red_sum[i].release(); ctx->red_wsum[i].release(); }
     if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
     if (ctx->d_out_inf) cudaFree(ctx->d_out_inf);
@@ -570,6 +571,37 @@ int accmsm_msm(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const 
     if (n == 0) return write_identity(ctx, B->curve, out_xy, out_inf);
     CU(ctx, cudaSetDevice(ctx->device));
     return msm_host_scalars(ctx, *B, offset, n, scalars, scalars_montgomery, nullptr, 0, out_xy, out_inf);
+}
+
+// VariableBaseMSM::multi_scalar_mul(&bases, &scalars) for bases that are not a registered key (the literal ark-ec
+// signature; in the reference: the O(log D) / O(n_inputs) linear combinations of commitments, e.g.
+// src/hp_as/mod.rs:391-406, src/ipa_pc_as/mod.rs:322-343).  Bases go up with the call and are dropped after it.
+int accmsm_msm_oneshot(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, const uint8_t *infinity, const uint64_t *scalars,
+                       int scalars_montgomery, size_t n, uint64_t out_xy[8], uint8_t *out_inf) {
+    if (!ctx || !out_xy || !out_inf || (curve != 0 && curve != 1) || (n && (!bases_xy || !scalars)) || n >= (size_t(1) << 31))
+        return fail_arg(ctx, "msm_oneshot: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (n == 0) return write_identity(ctx, curve, out_xy, out_inf);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    clear_marks(ctx);
+    CU(ctx, ctx->scalars.ensure(n * 32));
+    CU(ctx, ctx->oneshot_xy.ensure(n));
+    mark(ctx, ST_H2D, st);
+    CU(ctx, cudaMemcpyAsync(ctx->oneshot_xy.p, bases_xy, n * sizeof(affine_t), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    Bases B;
+    B.curve = curve; B.n = n; B.d_xy = ctx->oneshot_xy.p;
+    bool any_inf = false;
+    if (infinity) for (size_t i = 0; i < n && !any_inf; i++) any_inf = infinity[i] != 0;
+    if (any_inf) {
+        CU(ctx, ctx->misc.ensure(std::max<size_t>(n, 64 * 32)));
+        CU(ctx, cudaMemcpyAsync(ctx->misc.p, infinity, n, cudaMemcpyHostToDevice, st));
+        B.d_inf = ctx->misc.p;
+    }
+    int rc = msm_mem1(ctx, B, 0, n, ctx->scalars.p, scalars_montgomery, nullptr, 0, nullptr, true, st);
+    if (rc) return rc;
+    return fetch_affine(ctx, out_xy, out_inf, st);
 }
 
 int accmsm_msm_batch(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars,

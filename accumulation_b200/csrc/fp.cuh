@@ -113,6 +113,12 @@ constexpr uint32_t MOD_L0 = 1u, MOD_L7 = 0x40000000u;
 #if defined(__CUDACC__)
 static __constant__ uint32_t ACC_OPAQUE_ZERO;
 #endif
+// ACC_MUL_SHIFT_TOP = 1 computes q * 2^30 with two shifts on the ALU pipe instead of an IMAD.WIDE (96 -> 88 wide
+// multiplies per product).  Measured slower inside k_accumulate (2.30 vs 2.19 ms at 2^20): the kernel is bound by
+// issue slots of the whole instruction mix, not by the multiplier pipe alone.  Kept for the record, off.
+#ifndef ACC_MUL_SHIFT_TOP
+#define ACC_MUL_SHIFT_TOP 0
+#endif
 #ifndef ACC_MUL_WIDE_RIPPLES
 #define ACC_MUL_WIDE_RIPPLES 0
 #endif
@@ -251,7 +257,11 @@ template <int FIELD> struct Fp {
             od[0] = add_cc64(od[0], mulw(q, P::M1));
             od[1] = addc_cc64(od[1], mulw(q, P::M3));
             od[2] = addc_cc64(od[2], ACC_MUL_WIDE_RIPPLES >= 1 ? mulw(q, k0) : 0ull);
+#if ACC_MUL_SHIFT_TOP
+            od[3] = addc64(od[3], pack64(q << 30, q >> 2));     // q * 2^30 on the ALU pipe instead of an IMAD.WIDE
+#else
             od[3] = addc64(od[3], mulw(q, MOD_L7));
+#endif
         }
         fe_t r;  // (EV + OD 2^32) / 2^32, lo32(ev[0]) == 0
         r.l[0] = add_cc(hi32(ev[0]), lo32(od[0]));

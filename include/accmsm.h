@@ -78,6 +78,11 @@ int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_
  * BigInteger256.  n = 0 returns the identity.  ark-ec truncates to min(len): the caller passes that. */
 int accmsm_msm(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const uint64_t *scalars,
                int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf);
+/* The literal ark-ec call for bases that are NOT a registered key: VariableBaseMSM::multi_scalar_mul(&bases, &scalars)
+ * + into_affine().  In the reference these are the short linear combinations of commitments
+ * (src/hp_as/mod.rs:391-406, src/ipa_pc_as/mod.rs:322-343).  bases_xy: n x 8, infinity: n bytes or NULL. */
+int accmsm_msm_oneshot(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, const uint8_t *infinity,
+                       const uint64_t *scalars, int scalars_montgomery, size_t n, uint64_t out_xy[8], uint8_t *out_inf);
 /* k scalar vectors over the same bases (hp_as::decide commits a, b, a∘b: src/hp_as/mod.rs:910-918;
  * NARK prove commits z_A, z_B, z_C: src/r1cs_nark_as/r1cs_nark/mod.rs:216-218).
  * scalars: k x n x 4 u64, out_xy: k x 8, out_inf: k. */

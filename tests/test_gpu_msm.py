@@ -343,3 +343,19 @@ def test_precomputed_wide_windows(ctx, c):
         assert same_point(ctx.msm(B, const), cref.commit(0, pts, const))
     finally:
         B.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("n", [0, 1, 7, 42, 3000])
+def test_msm_oneshot_unregistered_bases(ctx, curve, n):
+    """the literal VariableBaseMSM::multi_scalar_mul(&bases, &scalars) signature (commitment linear combinations:
+    src/hp_as/mod.rs:391-406; 2 k + 2 terms of succinct_check at k = 20 is n = 42)"""
+    sf = cref.scalar_field(curve)
+    pts = cref.gen_points(curve, 900 + n, max(n, 1))[:n]
+    sc = cref.gen_scalars(sf, 901 + n, n, False)
+    inf = (np.arange(n) % 5 == 1).astype(np.uint8)
+    assert same_point(ctx.msm_oneshot(curve, pts, sc, montgomery=False), cref.msm_ark(curve, pts, sc) if n else point_result(curve, None))
+    if n:
+        assert same_point(ctx.msm_oneshot(curve, pts, sc, montgomery=False, infinity=inf), cref.msm_ark(curve, pts, sc, bases_inf=inf))
+        scm = cref.to_mont(sf, sc)
+        assert same_point(ctx.msm_oneshot(curve, pts, scm[: max(n - 1, 0)]), cref.msm_ark(curve, pts[: n - 1], sc[: n - 1]) if n > 1 else point_result(curve, None))
