@@ -12,8 +12,10 @@ struct alignas(16) affine_t { fe_t x, y; };            // 64 B, Montgomery coord
 struct alignas(16) xyzz_t { fe_t x, y, zz, zzz; };     // 128 B
 
 // CURVE 0 = Pallas (coordinates in Fp = field 0), CURVE 1 = Vesta (coordinates in Fq = field 1)
-template <int CURVE> struct Curve {
-    using F = Fp<CURVE == 0 ? 0 : 1>;
+// FT selects the field implementation: Fp (products inlined; throughput kernels) or FpCall (products behind a
+// call; latency-bound tail kernels, see fp.cuh).
+template <int CURVE, template <int> class FT = Fp> struct Curve {
+    using F = FT<CURVE == 0 ? 0 : 1>;
 
     static ACC_HD xyzz_t identity() {
         xyzz_t r;

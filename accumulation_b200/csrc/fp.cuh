@@ -297,4 +297,28 @@ template <int FIELD> struct Fp {
     }
 };
 
+// Fp with the product behind a real call.  The latency-bound tail kernels (one or a few warps walking through
+// dozens of point operations once) are dominated by instruction fetch when every product is inlined: an XYZZ add is
+// ~2500 instructions = 40 KB of straight-line code executed exactly once.  With the product out of line an add is a
+// few hundred instructions that stay in the instruction cache.  Throughput kernels keep the inlined Fp (measured:
+// k_accumulate is 1.5x slower with calls).
+template <int FIELD> struct FpCall : Fp<FIELD> {
+#if defined(__CUDACC__)
+    static __device__ __noinline__ fe_t mul(const fe_t &a, const fe_t &b) { return Fp<FIELD>::mul(a, b); }
+#else
+    static fe_t mul(const fe_t &a, const fe_t &b) { return Fp<FIELD>::mul(a, b); }
+#endif
+    static ACC_HD fe_t sqr(const fe_t &a) { return mul(a, a); }
+    static ACC_HD fe_t inv(const fe_t &a) {
+        using P = FieldParams<FIELD>;
+        fe_t acc = Fp<FIELD>::one();
+        const uint32_t e[8] = {0xffffffffu, P::M1 - 1u, P::M2, P::M3, 0u, 0u, 0u, MOD_L7};
+        for (int i = 254; i >= 0; i--) {
+            acc = mul(acc, acc);
+            if ((e[i >> 5] >> (i & 31)) & 1u) acc = mul(acc, a);
+        }
+        return acc;
+    }
+};
+
 }  // namespace accmsm

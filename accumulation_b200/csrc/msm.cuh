@@ -490,7 +490,7 @@ template <int CURVE, int BLK>
 __global__ void __launch_bounds__(BLK) k_sums(const xyzz_t *__restrict__ in, uint32_t in_set_stride,
                                               const uint32_t *__restrict__ offsets, xyzz_t *__restrict__ out,
                                               uint32_t out_set_stride, SumTasks tasks) {
-    using Cv = Curve<CURVE>;
+    using Cv = Curve<CURVE, FpCall>;
     __shared__ xyzz_t part[BLK / 32];
     uint32_t o = blockIdx.x, ti = 0;
     while (ti + 1 < tasks.ntasks && o >= tasks.t[ti].n_out) { o -= tasks.t[ti].n_out; ti++; }
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(BLK) k_sums(const xyzz_t *__restrict__ in, uin
 template <int CURVE>
 __global__ void __launch_bounds__(128) k_wsum_leaf(const xyzz_t *__restrict__ leaf, uint32_t leaf_set_stride, int nlevels,
                                                     uint32_t s0, xyzz_t *__restrict__ out) {
-    using Cv = Curve<CURVE>;
+    using Cv = Curve<CURVE, FpCall>;
     __shared__ xyzz_t W[4];
     __shared__ xyzz_t T0;
     const uint32_t set = blockIdx.x, a = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -587,7 +587,7 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
                          const xyzz_t *__restrict__ extra, uint32_t n_extra, int normalise,
                          xyzz_t *__restrict__ out_partial, affine_t *__restrict__ out_affine,
                          uint32_t *__restrict__ out_inf) {
-    using Cv = Curve<CURVE>;
+    using Cv = Curve<CURVE>;      // loops over one dbl / one sqr-mul body: already instruction-cache friendly
     if (threadIdx.x != 0) return;
     const uint32_t job = blockIdx.x;
     window_sums += (size_t)job * nwin;
