@@ -101,6 +101,9 @@ def run_reference(args, rank, world):
     """--impl reference: the ark-ec VariableBaseMSM restatement on host cores, same config / metric / unit."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is meant to use all the host threads it can
+    # (ark's rayon path does), so undo that before the OpenMP runtime of liboracle.so starts
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import cref
     n = 1 << LOG_N_PER_GPU
     pts = cref.gen_points(0, SEED, n)
@@ -112,7 +115,7 @@ def run_reference(args, rank, world):
         cref.msm_ark(0, pts, sc)
     dt = (time.perf_counter() - t0) / args.steps
     mpts = n / dt / 1e6
-    cores = cref.num_threads()
+    cores = ark_threads(n, cref.num_threads())
     print(json.dumps({
         "impl": "reference", "metric": "Pallas MSM Mpts/s @2^20", "value": round(mpts, 4), "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
@@ -121,7 +124,7 @@ def run_reference(args, rank, world):
                    "note": "CPU restatement of ark-ec 0.2.0 VariableBaseMSM (c = ln-rule, rayon-over-windows -> OpenMP over windows); "
                            "the Rust reference cannot be built in this image (no cargo)"},
         "cpu_baseline": {"value": round(mpts, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
-                         "sample": f"one full 2^{LOG_N_PER_GPU}-point MSM per step, canonical scalars"},
+                         "sample": f"one full 2^{LOG_N_PER_GPU}-point MSM per step (the per-GPU share of the workload), canonical scalars"},
         "e2e": {"value": round(mpts, 4), "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -297,7 +300,7 @@ def main():
         t0 = time.perf_counter()
         exp = cref.msm_ark(0, pts, sc_np)
         dt = time.perf_counter() - t0
-        cpu = {"value": round(count / dt / 1e6, 4), "unit": "Mpts/s", "cores": cref.num_threads(), "kind": "port",
+        cpu = {"value": round(count / dt / 1e6, 4), "unit": "Mpts/s", "cores": ark_threads(count, cref.num_threads()), "kind": "port",
                "sample": f"one full 2^{args.log_n}-point MSM (same bases and scalars as the GPU step), {dt:.2f} s"}
         if not args.no_verify:
             verified = bool(res[1] == exp[1] and np.array_equal(res[0], exp[0]) and np.array_equal(res_e2e[0], exp[0]))
@@ -345,6 +348,13 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ark_threads(n, omp_threads):
+    """ark-ec 0.2 parallelises over windows only: threads actually busy = min(threads, windows)"""
+    lg = max(n - 1, 1).bit_length()
+    c = 3 if n < 32 else lg * 69 // 100 + 2
+    return min(omp_threads, (255 + c - 1) // c)
 
 
 def table_window_bits(n):
