@@ -331,7 +331,8 @@ def main():
     if t_acc_ms > 0:
         achieved = 96.0 * count / (t_acc_ms * 1e-3) / 1e9
         out["roofline"] = {"kernel": "k_accumulate", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak,
-                           "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_kind": peak_kind,
+                           "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": measured_traffic(args.log_n, c, not args.no_precompute),
+                           "peak_kind": peak_kind,
                            "algorithmic_bytes": 96 * count, "kernel_ms": round(t_acc_ms, 4)}
         madds = count * nwin
         gmul = madds * MULS_PER_MADD / (t_acc_ms * 1e-3) / 1e9
@@ -355,6 +356,18 @@ def ark_threads(n, omp_threads):
     lg = max(n - 1, 1).bit_length()
     c = 3 if n < 32 else lg * 69 // 100 + 2
     return min(omp_threads, (255 + c - 1) // c)
+
+
+def measured_traffic(log_n, c, table):
+    """dram bytes per k_accumulate launch from the committed ncu capture, when it matches this configuration"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)["k_accumulate"]
+        if t["log_n"] == log_n and t["window_bits"] == c and bool(t["table"]) == bool(table):
+            return int(t["traffic_bytes"])
+    except Exception:
+        pass
+    return None
 
 
 def table_window_bits(n):
