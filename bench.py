@@ -257,6 +257,30 @@ def main():
                 assert ok
             decide[f"ipa_decide_tail_ms_2^{k}"] = round(statistics.median(ts), 4)
 
+    # ---- config 4: ipa-pc-as decide at degree 2^20 with the key sharded by point range over all ranks (strong scaling);
+    #      every rank expands its own coefficient range of h(X); one all-gather of 128-byte partials
+    if world > 1:
+        kk = 20
+        s_lo, s_cnt = shard_range(1 << kk, rank, world)
+        dkey = ctx.register_synthetic_bases(ab.PALLAS, SEED, s_cnt, first_index=s_lo)
+        dkey.precompute()
+        dsh = ShardedMSM(ctx, ab.PALLAS, dkey, 1 << kk, rank, world, device=str(dev))
+        ch = rand_scalars(kk, SEED + 77)
+        for _ in range(3):
+            dsh.ipa_final_key(ch, kk)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            fk = dsh.ipa_final_key(ch, kk)
+            barrier()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        tdec = torch.tensor([statistics.median(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tdec, op=dist.ReduceOp.MAX)
+        decide[f"ipa_decide_tail_sharded_ms_2^{kk}"] = round(float(tdec[0]), 4)
+        dkey.release()
+
     # ---- ipa-pc-as prove hot path: IpaPC::open on device (metric string: prove ms at degree 2^18), one GPU
     if rank == 0 and world == 1 and not args.no_open:
         import hashlib
@@ -268,7 +292,7 @@ def main():
             return _int_to_fe(1, int.from_bytes(h.digest()[:16], "little") | 1)
 
         for k in (18, 20):
-            if (1 << k) > count - 1:
+            if (1 << k) + 1 > key.n:        # needs the hiding generator after the 2^k generators
                 continue
             n = 1 << k
             ck = CommitterKey(key, n)
