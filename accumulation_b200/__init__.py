@@ -34,6 +34,34 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def pinned_array(shape, dtype=np.uint64) -> np.ndarray:
+    """numpy array backed by accmsm_host_alloc (page-locked); kept alive by the array's base object"""
+    lib = load()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.accmsm_host_alloc(C.c_size_t(max(nbytes, 1)))
+    if not ptr:
+        raise AccmsmError("accmsm_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+            self.buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+
+        def __del__(self):
+            lib.accmsm_host_free(C.c_void_p(self.p))
+    owner = _Owner(ptr)
+    arr = np.frombuffer(owner.buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED_OWNERS[arr.ctypes.data] = owner       # freed by release_pinned(arr) (or at interpreter exit)
+    return arr
+
+
+_PINNED_OWNERS = {}
+
+
+def release_pinned(arr: np.ndarray):
+    _PINNED_OWNERS.pop(arr.ctypes.data, None)
+
+
 class Context:
     """One accmsm_ctx bound to one GPU (one per process in the multi-GPU layout)."""
 
@@ -396,5 +424,5 @@ from .mirror import (  # noqa: E402
     ASForHadamardProducts, CommitterKey, InnerProductArgPC, PedersenCommitment, R1CSNark, SuccinctCheckPolynomial, matrix_vec_mul,
 )
 
-__all__ = ["Context", "Bases", "AccmsmError", "PALLAS", "VESTA", "FP", "FQ", "scalar_field", "PedersenCommitment",
+__all__ = ["Context", "Bases", "pinned_array", "release_pinned", "AccmsmError", "PALLAS", "VESTA", "FP", "FQ", "scalar_field", "PedersenCommitment",
            "CommitterKey", "InnerProductArgPC", "SuccinctCheckPolynomial", "ASForHadamardProducts", "R1CSNark", "matrix_vec_mul"]

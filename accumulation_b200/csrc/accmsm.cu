@@ -443,6 +443,15 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     delete ctx;
 }
 
+// Page-locked host memory for scalar / vector buffers: H2D from pinned memory runs at the PCIe rate (~53 GB/s
+// measured), from pageable memory at ~16 GB/s (2 ms instead of 0.6 ms for 2^20 scalars).
+void *accmsm_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, std::max<size_t>(bytes, 1)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+void accmsm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 int accmsm_set_window_bits(accmsm_ctx *ctx, int c) {
     if (!ctx || c < 0 || c > 16 || c == 1) return fail_arg(ctx, "window bits must be 0 (auto) or 2..16");
     ctx->window_bits = c;

@@ -42,6 +42,10 @@ int  accmsm_init(accmsm_ctx **out, int device);
 void accmsm_destroy(accmsm_ctx *ctx);
 const char *accmsm_strerror(int code);
 const char *accmsm_last_error(accmsm_ctx *ctx);
+/* Page-locked host buffers for scalars / vectors (optional): every host pointer of this API may be pageable, but
+ * H2D then runs at ~16 GB/s instead of the PCIe rate.  Returns NULL on failure. */
+void *accmsm_host_alloc(size_t bytes);
+void  accmsm_host_free(void *p);
 /* tuning knobs (0 = automatic): window bits c for the next MSMs */
 int  accmsm_set_window_bits(accmsm_ctx *ctx, int c);
 /* number of this library's kernels launched by ctx so far (bench.py reports it as gpu_launches) */

@@ -359,3 +359,14 @@ def test_msm_oneshot_unregistered_bases(ctx, curve, n):
         assert same_point(ctx.msm_oneshot(curve, pts, sc, montgomery=False, infinity=inf), cref.msm_ark(curve, pts, sc, bases_inf=inf))
         scm = cref.to_mont(sf, sc)
         assert same_point(ctx.msm_oneshot(curve, pts, scm[: max(n - 1, 0)]), cref.msm_ark(curve, pts[: n - 1], sc[: n - 1]) if n > 1 else point_result(curve, None))
+
+
+def test_pinned_host_buffers(ctx, keys):
+    """accmsm_host_alloc: page-locked scalar buffers give the same result (and the PCIe-rate H2D path)"""
+    pts, B = keys[0]
+    n = 5000
+    sc = cref.gen_scalars(cref.FQ, 950, n, True)
+    pin = ab.pinned_array((n, 4))
+    pin[:] = sc
+    assert same_point(ctx.msm(B, pin), cref.commit(0, pts[:n], sc))
+    ab.release_pinned(pin)
