@@ -145,6 +145,7 @@ struct MsmJobs {
     uint32_t njobs = 1;
     size_t offset[MAX_JOBS] = {0};     // first base of every job inside the key
     uint32_t tail_base = NONE_ID;      // index of the hiding generator when the last pair of every job is (H, r)
+    uint32_t map_log_h = NONE_ID;      // IPA round index map (msm.cuh), NONE_ID = identity
     MsmJobs() {}
     explicit MsmJobs(size_t off) { offset[0] = off; }
 };
@@ -154,6 +155,7 @@ MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, 
     sh.n = (uint32_t)n;
     sh.njobs = jobs.njobs;
     sh.tail_base = jobs.tail_base;
+    sh.map_log_h = jobs.map_log_h;
     for (int j = 0; j < MAX_JOBS; j++) sh.job_off[j] = j < (int)jobs.njobs ? (uint32_t)jobs.offset[j] : 0u;
     if (use_table(ctx, B, n)) {
         sh.c = B.pre_c;

@@ -1,10 +1,13 @@
 // Device side of IpaPC::open (ark-poly-commit ipa_pc; reference call sites
 // src/ipa_pc_as/mod.rs:454-462 (AS prove), :525-534 (index: default proof), examples/scaling-pc.rs:72-81).
-// The whole opening state -- coefficient vector, z-vector (1, z, z^2, ...) and the folded commitment key --
-// stays resident in HBM across the log2(D) rounds; per round only the two points (l, r) go to the host
-// sponge and one challenge comes back.
+// The opening state -- coefficient vector and z-vector (1, z, z^2, ...) -- stays resident in HBM across the log2(D)
+// rounds; per round only the two points (l, r) go to the host sponge and one challenge comes back.
 //   round:  l = cm_commit(key_l, coeffs_r) + <coeffs_r, z_l> h'     r = cm_commit(key_r, coeffs_l) + <coeffs_l, z_r> h'
-//   fold:   coeffs_l += xi^-1 coeffs_r ;  z_l += xi z_r ;  key_l += xi key_r  (normalised to affine)
+//   fold:   coeffs_l += xi^-1 coeffs_r ;  z_l += xi z_r ;  key_l += xi key_r
+// The key is never folded explicitly: the folded key of round j is a fixed linear combination of the registered key
+// (coefficients = products of the challenges so far), so every round's (l, r) is an MSM over the REGISTERED key with
+// scalars generated on the fly (IpaRoundScalars in msm.cuh) -- the window table applies, there is no Horner over
+// windows and no per-round scalar multiplication of n/2 generators; final_comm_key is one more such MSM.
 #pragma once
 #include "vec.cuh"
 
@@ -96,32 +99,6 @@ __global__ void __launch_bounds__(256) k_ipa_fold_scalars(uint8_t *__restrict__ 
     uint8_t *c0 = coeffs + (size_t)i * 32, *z0 = z + (size_t)i * 32;
     store_fe(c0, F::add(load_fe(c0), F::mul(xinv, load_fe(coeffs + (size_t)(i + h) * 32))));
     store_fe(z0, F::add(load_fe(z0), F::mul(x, load_fe(z + (size_t)(i + h) * 32))));
-}
-
-// dst[i] = src_l[i] + xi * src_r[i], normalised.  Every thread multiplies by the SAME scalar, so the
-// double-and-add bit loop is warp-uniform.  SFIELD = scalar field of the curve.
-template <int CURVE>
-__global__ void __launch_bounds__(128) k_ipa_fold_key(const affine_t *__restrict__ src_l, const affine_t *__restrict__ src_r,
-                                                       uint32_t h, const uint8_t *__restrict__ xi_mont, affine_t *__restrict__ dst) {
-    using Cv = Curve<CURVE>;
-    using S = Fp<CURVE == 0 ? 1 : 0>;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= h) return;
-    fe_t xi = S::from_mont(load_fe(xi_mont));
-    int top = 255;
-    while (top >= 0 && !((xi.l[top >> 5] >> (top & 31)) & 1u)) top--;
-    affine_t pr = load_affine(src_r + i);
-    xyzz_t acc = Cv::identity();
-#pragma unroll 1
-    for (int b = top; b >= 0; b--) {
-        acc = Cv::dbl(acc);
-        if ((xi.l[b >> 5] >> (b & 31)) & 1u) Cv::madd(acc, pr);
-    }
-    affine_t pl = load_affine(src_l + i);
-    Cv::madd(acc, pl);
-    affine_t a; uint32_t inf;
-    Cv::to_affine(acc, a, inf);      // the identity cannot be stored in a 64-byte key record: see accmsm_ipa_open_fold
-    store_fe(&dst[i].x, a.x); store_fe(&dst[i].y, a.y);
 }
 
 }  // namespace accmsm

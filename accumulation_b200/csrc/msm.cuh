@@ -50,7 +50,16 @@ struct MsmShape {
     // (base tail_base, randomizer) -- PedersenCommitment::commit(ck, elems, Some(r)) = MSM + r * hiding_generator
     // in the same pass.
     uint32_t tail_base;
+    // Optional index map (IPA opening rounds over the unfolded key): pair i of a job addresses base
+    // job_off + ((i >> map_log_h) << (map_log_h + 1)) + (i & (2^map_log_h - 1)), i.e. the lower (job_off = 0) or upper
+    // (job_off = 2^map_log_h) half of every block of 2^(map_log_h + 1) consecutive bases.  NONE_ID = identity map.
+    uint32_t map_log_h;
 };
+ACC_D uint32_t msm_base_index(const MsmShape &sh, uint32_t job, uint32_t i) {
+    if (sh.tail_base != NONE_ID && i == sh.n - 1) return sh.tail_base;
+    if (sh.map_log_h != NONE_ID) return sh.job_off[job] + ((i >> sh.map_log_h) << (sh.map_log_h + 1)) + (i & ((1u << sh.map_log_h) - 1u));
+    return sh.job_off[job] + i;
+}
 
 // ------------------------------------------------------------------------------------------------
 // vectorised loads / stores (128-bit, coalesced when consecutive threads touch consecutive records)
@@ -121,6 +130,28 @@ template <int SFIELD> struct IpaScalars {
     ACC_D fe_t canonical(uint32_t, uint32_t i) const { return Fp<SFIELD>::from_mont(coeff_mont(i)); }
 };
 
+// Scalars of one IPA opening round expressed over the UNFOLDED commitment key.  After j folds the
+// key is G^(j)[i] = sum_u C_j(u) G[u n_j + i] with C_j(u) = prod_{m <= j : bit (j - m) of u} xi_m (the h(X) coefficient
+// of the top j index bits), so with h = n_j / 2
+//     l = <a_R, G^(j)_L> = sum_{u, i' < h} a[h + i'] C_j(u) G[u n_j + i']          (job 0)
+//     r = <a_L, G^(j)_R> = sum_{u, i' < h} a[i']     C_j(u) G[u n_j + h + i']      (job 1)
+// are MSMs over the registered key (window table, no Horner over windows) and the key is never folded.
+template <int SFIELD> struct IpaRoundScalars {
+    const uint8_t *a;           // current coefficient vector, 2h Montgomery elements
+    const uint8_t *challenges;  // xi_1 .. xi_j, Montgomery
+    int j;
+    uint32_t log_h;
+    ACC_D fe_t canonical(uint32_t job, uint32_t i) const {
+        using F = Fp<SFIELD>;
+        const uint32_t h = 1u << log_h, ip = i & (h - 1u), u = i >> log_h;
+        fe_t acc = load_fe(a + (size_t)((job == 0 ? h : 0u) + ip) * 32);
+        for (int m = 1; m <= j; m++) {
+            if ((u >> (j - m)) & 1u) acc = F::mul(acc, load_fe(challenges + (size_t)(m - 1) * 32));
+        }
+        return F::from_mont(acc);
+    }
+};
+
 // bits [pos, pos + c) of a 256-bit little-endian integer, c <= 24
 ACC_D uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
     uint32_t limb = pos >> 5, off = pos & 31;
@@ -140,8 +171,7 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
     const uint32_t job = blockIdx.y;
     if (i >= sh.n) return;
     fe_t s = src.canonical(job, i);
-    const uint32_t base_index = (sh.tail_base != NONE_ID && i == sh.n - 1) ? sh.tail_base : sh.job_off[job] + i;
-    if (base_is_identity && base_is_identity[base_index]) s = Fp<0>::zero();   // identity bases contribute nothing
+    if (base_is_identity && base_is_identity[msm_base_index(sh, job, i)]) s = Fp<0>::zero();   // identity bases contribute nothing
     digits += (size_t)job * sh.nwin * sh.n;
     hist += (size_t)job * sh.sets_per_job * sh.nb;
     const uint32_t half = 1u << (sh.c - 1);
@@ -266,7 +296,7 @@ __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__
     if (i >= sh.n) return;
     digits += (size_t)job * sh.nwin * sh.n;
     cursor += (size_t)job * sh.sets_per_job * sh.nb;
-    const uint32_t base_index = (sh.tail_base != NONE_ID && i == sh.n - 1) ? sh.tail_base : sh.job_off[job] + i;
+    const uint32_t base_index = msm_base_index(sh, job, i);
     const unsigned am = __activemask();
     const uint32_t lane = threadIdx.x & 31, leader = __ffs(am) - 1;
     const uint32_t rank = __popc(am & ((1u << lane) - 1u));

@@ -144,8 +144,9 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
  *     finish() -> (final_comm_key, c)
  * round:  l = cm_commit(key_l, coeffs_r) + <coeffs_r, z_l> h'      r = cm_commit(key_r, coeffs_l) + <coeffs_l, z_r> h'
  * fold :  coeffs_l += xi^-1 coeffs_r;  z_l += xi z_r;  key_l += xi key_r (batch-normalised)
- * fold only enqueues; finish releases the session (also on error).  A folded generator equal to the identity
- * (probability ~2^-255 for sponge challenges) is not representable and is not detected. */
+ * fold only enqueues; finish releases the session (also on error).  The key is never folded on the device: every
+ * round's (l, r) and the final key are MSMs over the registered key (window table if built) with scalars
+ * coefficient x product-of-challenges generated in registers, so results equal the folded-key computation exactly. */
 int accmsm_ipa_open_begin(accmsm_ctx *ctx, uint64_t handle, const uint64_t *coeffs_mont, size_t n_coeffs, int k,
                           const uint64_t point_mont[4], const uint64_t h_prime_xy[8], uint64_t *session);
 /* Same session, but the polynomial being opened is built on the device: AtomicASForInnerProductArgPC::prove opens
