@@ -129,12 +129,13 @@ uint32_t pick_window_bits(const accmsm_ctx *ctx, size_t n) {
     return (uint32_t)std::min(16, std::max(4, c));
 }
 
-// The window table is used when the MSM is large enough for the table's (fixed) bucket count to pay off
-// and no explicit window override asks for something else.
+// The window table is used whenever the key has one (unless an explicit window override asks for something else),
+// also for MSMs much shorter than the key: a short MSM is bound by the latency of its tail, and the table path has no
+// Horner over windows (~256 dependent doublings, ~0.9 ms), only a reduction over mostly empty buckets.
 bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
+    (void)n;
     if (!B.d_table) return false;
-    if (ctx->window_bits && (uint32_t)ctx->window_bits != B.pre_c) return false;
-    return n >= (size_t(1) << (B.pre_c > 4 ? B.pre_c - 4 : 0));
+    return !ctx->window_bits || (uint32_t)ctx->window_bits == B.pre_c;
 }
 
 #ifndef RED_L0_BLK
@@ -517,8 +518,8 @@ int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, u
 }
 
 int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
-    if (!ctx || window_bits < 0 || (window_bits && (window_bits < 8 || window_bits > 21)))
-        return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 8..21");
+    if (!ctx || window_bits < 0 || (window_bits && (window_bits < 4 || window_bits > 21)))
+        return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 4..21");
     std::lock_guard<std::mutex> lock(ctx->mu);
     auto it = ctx->bases.find(handle);
     if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }
@@ -531,7 +532,7 @@ int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
     // windows mean fewer bucket insertions, and the single bucket set keeps the reduction affordable
     uint32_t lg = 0;
     while ((size_t(1) << (lg + 1)) <= B.n) lg++;
-    uint32_t c = window_bits ? (uint32_t)window_bits : std::min(20u, std::max(12u, lg));
+    uint32_t c = window_bits ? (uint32_t)window_bits : std::min(20u, std::max(8u, lg));
     uint32_t nwin = (256 + c - 1) / c;
     if ((size_t)nwin * B.n >= (size_t(1) << 31)) return fail_arg(ctx, "precompute_bases: windows * n must be < 2^31");
     affine_t *table = nullptr;

@@ -644,7 +644,7 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
 // keys are fixed for the life of a prover (trim / index time), so the MSM then needs a single bucket set,
 // one bucket reduction and no window doublings.
 // ------------------------------------------------------------------------------------------------
-constexpr int MAX_PRE_WINDOWS = 32;
+constexpr int MAX_PRE_WINDOWS = 64;   // c >= 4
 template <int CURVE>
 __global__ void __launch_bounds__(128) k_precompute(const affine_t *__restrict__ bases, uint32_t n, uint32_t c,
                                                      uint32_t nwin, affine_t *__restrict__ table) {

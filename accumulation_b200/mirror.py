@@ -22,11 +22,15 @@ class CommitterKey:
     num_generators: int
 
     @staticmethod
-    def new(ctx, curve: int, generators_xy, hiding_generator_xy=None) -> "CommitterKey":
+    def new(ctx, curve: int, generators_xy, hiding_generator_xy=None, precompute: bool = False) -> "CommitterKey":
+        """precompute: also build the window table (once per key; trim / index time in the reference)"""
         gens = np.ascontiguousarray(generators_xy, dtype=np.uint64).reshape(-1, 8)
         allb = gens if hiding_generator_xy is None else np.concatenate(
             [gens, np.ascontiguousarray(hiding_generator_xy, dtype=np.uint64).reshape(1, 8)])
-        return CommitterKey(ctx.register_bases(curve, allb), gens.shape[0])
+        bases = ctx.register_bases(curve, allb)
+        if precompute:
+            bases.precompute()
+        return CommitterKey(bases, gens.shape[0])
 
     def supported_num_elems(self) -> int:   # src/hp_as/mod.rs:129,681
         return self.num_generators

@@ -396,7 +396,7 @@ def measured_traffic(log_n, c, table):
 
 def table_window_bits(n):
     """mirror of the automatic rule in accmsm_precompute_bases (reporting only)"""
-    return min(20, max(12, max(n, 1).bit_length() - 1))
+    return min(20, max(8, max(n, 1).bit_length() - 1))
 
 
 def ctx_window_bits(n):

@@ -61,7 +61,7 @@ def test_ipa_open_golden_vectors(ctx):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-@pytest.mark.parametrize("k,precompute", [(0, False), (1, False), (5, False), (10, False), (13, True)])
+@pytest.mark.parametrize("k,precompute", [(0, False), (1, False), (1, True), (4, True), (5, False), (10, False), (10, True), (13, True)])
 def test_ipa_open_vs_oracle_and_verifies(ctx, curve, k, precompute):
     """config 1 of BASELINE.json is k = 10 (degree 2^10 - 1); polynomials shorter than the key are zero-padded."""
     sf = cref.scalar_field(curve)
