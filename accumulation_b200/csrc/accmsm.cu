@@ -19,8 +19,9 @@ using namespace accmsm;
 
 namespace {
 
-enum Stage { ST_H2D = 0, ST_DIGITS, ST_SCAN, ST_SCATTER, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_FINISH, ST_D2H, ST_COUNT };
-const char *STAGE_NAMES[ST_COUNT] = {"h2d", "digits", "scan", "scatter", "accumulate", "fixup", "bucket_reduce", "finish", "d2h"};
+enum Stage { ST_H2D = 0, ST_DIGITS, ST_SCAN, ST_SCATTER, ST_ACCUMULATE, ST_FIXUP, ST_REDUCE, ST_FINISH, ST_D2H, ST_VEC, ST_VEC_D2H, ST_COUNT };
+const char *STAGE_NAMES[ST_COUNT] = {"h2d", "digits", "scan", "scatter", "accumulate", "fixup", "bucket_reduce", "finish", "d2h",
+                                     "vec_kernel", "vec_d2h"};
 
 struct Bases {
     int curve = 0;

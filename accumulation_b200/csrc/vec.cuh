@@ -15,28 +15,42 @@ struct VecPtrs {
     uint32_t len[VEC_MAX_INPUTS];
 };
 
+// h(X) coefficients via two half tables: coeff[j] = hi[j >> L] * lo[j & (2^L - 1)], where lo / hi hold the products
+// of the challenges selected by the low L / high k - L index bits.  One product per coefficient instead of ~k/2
+// (the element-wise kernel is then bound by its 32-byte store, not by the multiplier); the tables (<= 2 x 2^11 entries
+// per polynomial) stay in L1/L2.  alphas (nullable) are folded into the hi tables: hi_i *= alpha_i.
 template <int FIELD>
-__global__ void __launch_bounds__(256) k_compute_coeffs(const uint8_t *__restrict__ challenges, int k, uint8_t *__restrict__ out) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= (1u << k)) return;
-    IpaScalars<FIELD> src{challenges, k, 0};
-    store_fe(out + (size_t)j * 32, src.coeff_mont(j));
+__global__ void __launch_bounds__(256) k_coeff_tables(const uint8_t *__restrict__ challenges, int m, int k, int L,
+                                                       const uint8_t *__restrict__ alphas, uint8_t *__restrict__ lo,
+                                                       uint8_t *__restrict__ hi) {
+    using F = Fp<FIELD>;
+    const uint32_t n_lo = 1u << L, n_hi = 1u << (k - L), per = n_lo + n_hi;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * (uint32_t)m) return;
+    const uint32_t i = t / per, e = t % per;
+    const uint8_t *ch = challenges + (size_t)i * k * 32;
+    const bool is_lo = e < n_lo;
+    const uint32_t idx = is_lo ? e : e - n_lo;
+    const int b0 = is_lo ? 0 : L, nb = is_lo ? L : k - L;
+    fe_t acc = (!is_lo && alphas) ? load_fe(alphas + (size_t)i * 32) : F::one();
+    for (int b = 0; b < nb; b++) {             // index bit b0 + b  <->  challenge k - 1 - (b0 + b)
+        if ((idx >> b) & 1u) acc = F::mul(acc, load_fe(ch + (size_t)(k - 1 - (b0 + b)) * 32));
+    }
+    store_fe((is_lo ? lo + (size_t)i * n_lo * 32 : hi + (size_t)i * n_hi * 32) + (size_t)idx * 32, acc);
 }
-
-// out[j] = random_poly[j] + sum_i alpha_i * coeffs_i[j]
+// out[j] = random_poly[j] (j < n_random) + sum_i hi_i[j >> L] * lo_i[j & mask]
 template <int FIELD>
-__global__ void __launch_bounds__(256) k_combine_check_polys(const uint8_t *__restrict__ challenges, int m, int k,
-                                                              const uint8_t *__restrict__ alphas,
-                                                              const uint8_t *__restrict__ random_poly, uint32_t n_random,
-                                                              uint8_t *__restrict__ out) {
+__global__ void __launch_bounds__(256) k_coeffs_from_tables(const uint8_t *__restrict__ lo, const uint8_t *__restrict__ hi, int m,
+                                                             int k, int L, const uint8_t *__restrict__ random_poly,
+                                                             uint32_t n_random, uint8_t *__restrict__ out) {
     using F = Fp<FIELD>;
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (1u << k)) return;
-    fe_t acc = (random_poly && j < n_random) ? load_fe_nc(random_poly + (size_t)j * 32) : F::zero();
-    for (int i = 0; i < m; i++) {
-        IpaScalars<FIELD> src{challenges + (size_t)i * k * 32, k, 0};
-        acc = F::add(acc, F::mul(src.coeff_mont(j), load_fe(alphas + (size_t)i * 32)));
-    }
+    const uint32_t n_lo = 1u << L, n_hi = 1u << (k - L), jl = j & (n_lo - 1u), jh = j >> L;
+    fe_t acc = F::mul(load_fe(hi + (size_t)jh * 32), load_fe(lo + (size_t)jl * 32));
+    for (int i = 1; i < m; i++)
+        acc = F::add(acc, F::mul(load_fe(hi + ((size_t)i * n_hi + jh) * 32), load_fe(lo + ((size_t)i * n_lo + jl) * 32)));
+    if (random_poly && j < n_random) acc = F::add(acc, load_fe_nc(random_poly + (size_t)j * 32));
     store_fe(out + (size_t)j * 32, acc);
 }
 
@@ -52,25 +66,27 @@ template <int FIELD> ACC_D fe_t block_sum(fe_t v, fe_t *sh) {
     return sh[0];
 }
 
-// polynomial evaluation: thread t folds POLY_CHUNK coefficients by Horner and scales by z^(t*POLY_CHUNK)
-constexpr int POLY_CHUNK = 16;
+// polynomial evaluation: thread t folds `chunk` coefficients by Horner and scales by z^(t*chunk); chunk = 16 up to 2^20
+// coefficients (more threads: latency), 64 beyond (fewer products per coefficient: throughput)
+inline uint32_t poly_chunk(size_t n) { return n > (size_t(1) << 20) ? 64u : 16u; }
 template <int FIELD>
 __global__ void __launch_bounds__(256) k_poly_eval_partial(const uint8_t *__restrict__ coeffs, uint32_t n,
-                                                            const uint8_t *__restrict__ z_ptr, uint8_t *__restrict__ partials) {
+                                                            const uint8_t *__restrict__ z_ptr, uint8_t *__restrict__ partials,
+                                                            uint32_t chunk) {
     using F = Fp<FIELD>;
     __shared__ fe_t sh[256];
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     fe_t z = load_fe(z_ptr);
     fe_t term = F::zero();
-    uint32_t lo = t * POLY_CHUNK;
+    uint32_t lo = t * chunk;
     if (lo < n) {
-        uint32_t hi = lo + POLY_CHUNK < n ? lo + POLY_CHUNK : n;
+        uint32_t hi = lo + chunk < n ? lo + chunk : n;
         fe_t acc = F::zero();
         for (uint32_t j = hi; j-- > lo;) acc = F::add(F::mul(acc, z), load_fe_nc(coeffs + (size_t)j * 32));
-        // z^(t * POLY_CHUNK): zc = z^16, then square-and-multiply on t
+        // z^(t * chunk): zc = z^chunk, then square-and-multiply on t
         fe_t zc = z;
 #pragma unroll 1
-        for (int i = 0; i < 4; i++) zc = F::sqr(zc);
+        for (uint32_t i = 1; i < chunk; i <<= 1) zc = F::sqr(zc);
         fe_t pw = F::one();
         for (uint32_t e = t; e; e >>= 1) {
             if (e & 1u) pw = F::mul(pw, zc);
