@@ -113,9 +113,11 @@ template <int CURVE, template <int> class FT = Fp> struct Curve {
 
     // Normalise to ark-ec's affine image: (x, y, infinity); the identity is (0, 1, true).
     // With t = ZZZ^-1:  ZZ^-1 = ZZ^2 t^2 (since ZZ^3 = ZZZ^2), so x = X ZZ^2 t^2, y = Y t.
+    // GCD = true: binary-GCD inversion (single-thread tails); false: Fermat ladder (no divergence across lanes)
+    template <bool GCD = false>
     static ACC_HD void to_affine(const xyzz_t &p, affine_t &out, uint32_t &inf) {
         if (is_identity(p)) { out.x = F::zero(); out.y = F::one(); inf = 1; return; }
-        fe_t t = F::inv(p.zzz);
+        fe_t t = GCD ? F::inv_gcd(p.zzz) : F::inv(p.zzz);
         fe_t zt = F::mul(p.zz, t);
         out.x = F::mul(p.x, F::sqr(zt));
         out.y = F::mul(p.y, t);

@@ -285,6 +285,69 @@ template <int FIELD> struct Fp {
     }
     static ACC_HD fe_t to_mont(const fe_t &a) { return mul(a, r2()); }
 
+    // R^3 mod m (for inv_gcd: the inverse of the Montgomery image x = a R is a^-1 R^-1; times R^3 / R gives a^-1 R)
+    static ACC_HD fe_t r3() {
+        fe_t r;
+        if (FIELD == 0) {
+            r.l[0] = 0x3a9e10f9u; r.l[1] = 0xf185a599u; r.l[2] = 0x6ac5b1d1u; r.l[3] = 0xf6a68f3bu;
+            r.l[4] = 0x353fd42cu; r.l[5] = 0xdf8d1014u; r.l[6] = 0x2d2d9910u; r.l[7] = 0x2ae30922u;
+        } else {
+            r.l[0] = 0x249dae4cu; r.l[1] = 0x008b421cu; r.l[2] = 0xdba41326u; r.l[3] = 0xe13bda50u;
+            r.l[4] = 0x8e15cb63u; r.l[5] = 0x88fececbu; r.l[6] = 0x6e6792c8u; r.l[7] = 0x07dd97a0u;
+        }
+        return r;
+    }
+    // Inversion by the binary extended Euclidean algorithm (Stein): ~380 shift steps and ~180 subtractions on 8 limbs,
+    // about a third of the ~254 squarings + ~64 products of the Fermat ladder below.  Data-dependent control flow: meant
+    // for single-thread tails (k_finish normalises one point per MSM); kernels where every lane inverts its own value
+    // keep inv() (no divergence).  inv_gcd(0) = 0.
+    static ACC_HD fe_t inv_gcd(const fe_t &a) {
+        if (is_zero(a)) return zero();
+        fe_t u = a, v, b = zero(), c = zero();
+#pragma unroll
+        for (int i = 0; i < 8; i++) v.l[i] = mod_limb(i);
+        b.l[0] = 1u;                                   // b x == u, c x == v (mod m) with x the integer image of a
+        auto is_one = [](const fe_t &t) { return t.l[0] == 1u && (t.l[1] | t.l[2] | t.l[3] | t.l[4] | t.l[5] | t.l[6] | t.l[7]) == 0u; };
+        auto shr1 = [](fe_t &t, uint32_t top) {
+#pragma unroll
+            for (int i = 0; i < 7; i++) t.l[i] = (t.l[i] >> 1) | (t.l[i + 1] << 31);
+            t.l[7] = (t.l[7] >> 1) | (top << 31);
+        };
+        auto halve_mod = [&](fe_t &t) {               // t / 2 mod m for t < m
+            uint32_t carry = 0;
+            if (t.l[0] & 1u) {
+                t.l[0] = add_cc(t.l[0], MOD_L0);
+                t.l[1] = addc_cc(t.l[1], P::M1);
+                t.l[2] = addc_cc(t.l[2], P::M2);
+                t.l[3] = addc_cc(t.l[3], P::M3);
+                t.l[4] = addc_cc(t.l[4], 0u);
+                t.l[5] = addc_cc(t.l[5], 0u);
+                t.l[6] = addc_cc(t.l[6], 0u);
+                t.l[7] = addc_cc(t.l[7], MOD_L7);
+                carry = addc(0u, 0u);
+            }
+            shr1(t, carry);
+        };
+        while (!is_one(u) && !is_one(v)) {
+            while (!(u.l[0] & 1u)) { shr1(u, 0u); halve_mod(b); }
+            while (!(v.l[0] & 1u)) { shr1(v, 0u); halve_mod(c); }
+            fe_t d;                                    // d = u - v, borrow tells which is larger
+            d.l[0] = sub_cc(u.l[0], v.l[0]);
+#pragma unroll
+            for (int i = 1; i < 8; i++) d.l[i] = subc_cc(u.l[i], v.l[i]);
+            uint32_t borrow = subc(0u, 0u);
+            if (!borrow) { u = d; b = sub(b, c); }
+            else {
+                v.l[0] = sub_cc(v.l[0], u.l[0]);
+#pragma unroll
+                for (int i = 1; i < 7; i++) v.l[i] = subc_cc(v.l[i], u.l[i]);
+                v.l[7] = subc(v.l[7], u.l[7]);
+                c = sub(c, b);
+            }
+        }
+        return mul(is_one(u) ? b : c, r3());
+    }
+
     // a^(m-2) (Fermat); inv(0) = 0.  m - 2 has limbs [0xffffffff, M1-1, M2, M3, 0, 0, 0, 2^30].
     static ACC_HD fe_t inv(const fe_t &a) {
         fe_t acc = one();

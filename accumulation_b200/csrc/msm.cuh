@@ -631,7 +631,7 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
     if (out_partial) store_xyzz(out_partial + job, acc);
     if (normalise) {
         affine_t a; uint32_t inf;
-        Cv::to_affine(acc, a, inf);
+        Cv::template to_affine<true>(acc, a, inf);
         store_fe(&out_affine[job].x, a.x); store_fe(&out_affine[job].y, a.y);
         out_inf[job] = inf;
     }

@@ -18,6 +18,7 @@ template <int F> static void binop(int op, const uint32_t *a, const uint32_t *b,
             case 5: r = Fp<F>::from_mont(x); break;
             case 6: r = Fp<F>::to_mont(x); break;
             case 7: r = Fp<F>::neg(x); break;
+            case 8: r = Fp<F>::inv_gcd(x); break;
             default: r = x;
         }
         memcpy(o + 8 * i, r.l, 32);

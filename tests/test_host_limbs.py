@@ -50,6 +50,11 @@ def test_field_limb_algorithms(shim, field):
     assert (fe_op(shim, field, 7, a) == cref.fe_sub(field, np.zeros_like(a), a)).all()
     assert (fe_op(shim, field, 4, a[:200]) == cref.fe_inv(field, a[:200])).all()
     assert (fe_op(shim, field, 4, ea) == cref.fe_inv(field, ea)).all()
+    # binary-GCD inversion (used by the single-thread normalisation in k_finish) == Fermat == oracle
+    assert (fe_op(shim, field, 8, a[:3000]) == cref.fe_inv(field, a[:3000])).all()
+    assert (fe_op(shim, field, 8, ea) == cref.fe_inv(field, ea)).all()
+    small = cref.to_mont(field, cref.ints_to_arr(list(range(0, 70)) + [m - i for i in range(1, 70)] + [1 << i for i in range(0, 255, 7)]))
+    assert (fe_op(shim, field, 8, small) == cref.fe_inv(field, small)).all()
 
 
 def ec_sum(lib, curve, pts, neg, mode):
