@@ -279,6 +279,21 @@ def main():
         tdec = torch.tensor([statistics.median(ts)], dtype=torch.float64, device=dev)
         dist.all_reduce(tdec, op=dist.ReduceOp.MAX)
         decide[f"ipa_decide_tail_sharded_ms_2^{kk}"] = round(float(tdec[0]), 4)
+        # config 5 strong scaling: ONE 2^20-point MSM sharded over all ranks (scalars resident in HBM)
+        d_sl = d_sc[:s_cnt]
+        for _ in range(3):
+            dsh.msm_dev(d_sl, montgomery=False)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            dsh.msm_dev(d_sl, montgomery=False)
+            barrier()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        tdec = torch.tensor([statistics.median(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tdec, op=dist.ReduceOp.MAX)
+        decide[f"msm_sharded_strong_ms_2^{kk}"] = round(float(tdec[0]), 4)
         dkey.release()
 
     # ---- ipa-pc-as prove hot path: IpaPC::open on device (metric string: prove ms at degree 2^18), one GPU
