@@ -370,3 +370,30 @@ def test_pinned_host_buffers(ctx, keys):
     pin[:] = sc
     assert same_point(ctx.msm(B, pin), cref.commit(0, pts[:n], sc))
     ab.release_pinned(pin)
+
+
+def test_error_codes_never_abort(ctx, keys):
+    """error convention of the boundary: 0 or a negative ACCMSM_E_* code plus a message, never a crash"""
+    import ctypes as C
+    pts, B = keys[0]
+    lib, h = ctx._lib, ctx._h
+    out = np.empty(8, np.uint64); inf = C.c_uint8(0)
+    sc = cref.gen_scalars(cref.FQ, 1, 10, True)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.accmsm_msm(h, C.c_uint64(987654321), C.c_size_t(0), C.c_size_t(10), p(sc), 1, p(out), C.byref(inf)) == -3      # E_HANDLE
+    assert lib.accmsm_msm(h, C.c_uint64(B.handle), C.c_size_t(B.n - 3), C.c_size_t(10), p(sc), 1, p(out), C.byref(inf)) == -2  # range
+    assert b"range" in lib.accmsm_last_error(h)
+    assert lib.accmsm_msm(h, C.c_uint64(B.handle), C.c_size_t(0), C.c_size_t(10), None, 1, p(out), C.byref(inf)) == -2          # null scalars
+    assert lib.accmsm_commit(h, C.c_uint64(B.handle), C.c_size_t(10), p(sc), C.c_size_t(B.n + 5), p(sc), p(out), C.byref(inf)) == -2
+    assert lib.accmsm_ipa_final_key(h, C.c_uint64(B.handle), p(sc), 31, p(out), C.byref(inf)) == -2                             # k too large
+    assert lib.accmsm_ipa_final_key(h, C.c_uint64(B.handle), p(cref.gen_scalars(cref.FQ, 2, 20, True)), 20, p(out), C.byref(inf)) == -2   # key shorter than 2^k
+    assert lib.accmsm_set_window_bits(h, 1) == -2 and lib.accmsm_set_window_bits(h, 40) == -2
+    assert lib.accmsm_precompute_bases(h, C.c_uint64(B.handle), 30) == -2
+    assert lib.accmsm_release_bases(h, C.c_uint64(555)) == -3
+    sess = C.c_uint64(0)
+    assert lib.accmsm_ipa_open_round(h, C.c_uint64(4242), p(out), C.byref(inf), p(out), C.byref(inf)) == -3
+    assert lib.accmsm_ipa_open_begin(h, C.c_uint64(B.handle), p(sc), C.c_size_t(10), 2, p(sc), p(out), C.byref(sess)) == -2     # 10 coeffs > 2^2
+    with pytest.raises(ab.AccmsmError):
+        ctx.msm(B, sc, offset=B.n)
+    # the context still works afterwards
+    assert same_point(ctx.msm(B, sc), cref.commit(0, pts[:10], sc))
