@@ -116,6 +116,29 @@ class InnerProductArgPC:
         return comm_key.bases.ctx.commit(comm_key.bases, el, hiding_index=idx, randomizer_mont=randomizer)
 
     @staticmethod
+    def succinct_check_equation(ctx, curve: int, comm, point, value, l_vec, r_vec, round_challenges, h_prime_xy, final_comm_key_xy, c) -> bool:
+        """Group equation of IpaPC::succinct_check (SURVEY.md App. A.2; src/ipa_pc_as/mod.rs:198-205) with the transcript
+        values supplied by the host:  C + v h' + sum_i (xi_i^-1 l_i + xi_i r_i) == c final_comm_key + (h(z) c) h'.
+        One 2k + 3 term MSM over unregistered points (accmsm_msm_oneshot) whose result must be the identity; the O(k)
+        scalar preparation (inverses, h(z)) is host arithmetic like in the reference.  comm = (xy, inf)."""
+        from . import scalar_field
+        f = scalar_field(curve)
+        m = _MODULI[f]
+        xis = [_fe_to_int(f, x) for x in np.asarray(round_challenges, dtype=np.uint64).reshape(-1, 4)]
+        k = len(xis)
+        z, v, cc = _fe_to_int(f, point), _fe_to_int(f, value), _fe_to_int(f, c)
+        hz = 1
+        for i, xi in enumerate(xis, start=1):
+            hz = hz * (1 + xi * pow(z, 1 << (k - i), m)) % m
+        bases = [np.asarray(comm[0], dtype=np.uint64)] + [np.asarray(p[0], dtype=np.uint64) for p in l_vec] + \
+                [np.asarray(p[0], dtype=np.uint64) for p in r_vec] + [np.asarray(h_prime_xy, dtype=np.uint64), np.asarray(final_comm_key_xy, dtype=np.uint64)]
+        inf = [int(comm[1])] + [int(p[1]) for p in l_vec] + [int(p[1]) for p in r_vec] + [0, 0]
+        scal = [1] + [pow(xi, -1, m) for xi in xis] + xis + [(v - hz * cc) % m, (-cc) % m]
+        sc = np.array([[(s_ >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for s_ in scal], dtype=np.uint64)
+        _, res_inf = ctx.msm_oneshot(curve, np.array(bases), sc, montgomery=False, infinity=np.array(inf, dtype=np.uint8))
+        return bool(res_inf)
+
+    @staticmethod
     def check_final_key(vk: CommitterKey, check_poly_challenges, final_comm_key_xy, final_comm_key_inf: int = 0) -> bool:
         """Tail of check_individual_opening_challenges (reached from decide, src/ipa_pc_as/mod.rs:836-845):
         final_key = cm_commit(vk.comm_key, h.compute_coeffs()); accept iff final_key == proof.final_comm_key."""

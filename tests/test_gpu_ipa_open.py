@@ -88,6 +88,11 @@ def test_ipa_open_vs_oracle_and_verifies(ctx, curve, k, precompute):
         v = cref.poly_evaluate(sf, padded, z)
         lx, rx, xs = np.array([p[0] for p in l_vec]), np.array([p[0] for p in r_vec]), np.array(chs)
         assert cref.ipa_succinct_check(curve, comm, z, v, lx, rx, xs, hp, fk, c)
+        # the same equation on the device (one 2k + 3 term one-shot MSM == identity), accept and reject
+        assert ab.InnerProductArgPC.succinct_check_equation(ctx, curve, comm, z, v, l_vec, r_vec, xs, hp, fk, c)
+        v_bad = v.copy(); v_bad[0] ^= np.uint64(1)
+        assert not ab.InnerProductArgPC.succinct_check_equation(ctx, curve, comm, z, v_bad, l_vec, r_vec, xs, hp, fk, c)
+        assert not ab.InnerProductArgPC.succinct_check_equation(ctx, curve, comm, z, v, r_vec, l_vec, xs, hp, fk, c)
         # the decider's half of check(): final_key == cm_commit(key, h.compute_coeffs())  (GPU, fused K3 -> K2)
         assert ab.InnerProductArgPC.check_final_key(ck, xs, fk, 0)
         bad = fk.copy(); bad[3] ^= np.uint64(2)
