@@ -139,6 +139,9 @@ bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
     return !ctx->window_bits || (uint32_t)ctx->window_bits == B.pre_c;
 }
 
+constexpr uint32_t ACC_WARP_MAX_KEYS = 8192;        // warp-per-bucket accumulation up to this many buckets ...
+constexpr size_t ACC_WARP_MAX_ENTRIES = 1u << 16;   // ... and bucket insertions (measured crossover with the balanced kernel: 2^12 points)
+
 #ifndef RED_L0_BLK
 #define RED_L0_BLK 32     // threads per row / column sum of the first reduction level (one warp: 16-32 serial adds + 5 shuffle steps; measured best of 32/64/128/256)
 #endif
@@ -227,7 +230,13 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
         ctx->launches++;
     }
     mark(ctx, ST_ACCUMULATE, st);
-    {
+    if (sh.nkeys <= ACC_WARP_MAX_KEYS && n_entries <= ACC_WARP_MAX_ENTRIES) {
+        // short MSM: one warp per bucket, no slice merging (k_accumulate_warp in msm.cuh)
+        uint32_t blocks = (sh.nkeys * 32 + 255) / 256;
+        k_accumulate_warp<CURVE><<<blocks, 256, 0, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p, points, ctx->buckets.p);
+        ctx->launches++;
+        mark(ctx, ST_FIXUP, st);
+    } else {
         // grid: a whole number of resident waves, shrunk for small inputs so every thread still gets a
         // few entries (upper bound n * nwin; the real count is only known on the device)
         int per_sm = ctx->acc_ctas_per_sm[CURVE];
