@@ -538,11 +538,13 @@ int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (B.d_table) { cudaFree(B.d_table); B.d_table = nullptr; B.pre_c = B.pre_nwin = 0; }
     if (B.n == 0) return ACCMSM_OK;
-    // auto: about one bucket per two points, measured best at 2^20 (profiles/r01b_window_sweep.txt): fewer
-    // windows mean fewer bucket insertions, and the single bucket set keeps the reduction affordable
+    // auto: measured best per key size (profiles/r01l_window_rule.txt).  Scalars are < 2^254, so what counts is
+    // ceil(254 / c) non-empty windows and the bucket count 2^(c-1) of the single bucket set: c = 17 has 15 working
+    // windows (the 16th covers bit 255 only) over 2^16 buckets and wins from 2^15 to 2^19 points; c = 20 (13 windows,
+    // 2^19 buckets) from 2^20 on, where the insertions dominate the reduction.
     uint32_t lg = 0;
     while ((size_t(1) << (lg + 1)) <= B.n) lg++;
-    uint32_t c = window_bits ? (uint32_t)window_bits : std::min(20u, std::max(8u, lg));
+    uint32_t c = window_bits ? (uint32_t)window_bits : lg >= 20 ? 20u : lg >= 15 ? 17u : lg >= 13 ? 15u : 10u;
     uint32_t nwin = (256 + c - 1) / c;
     if ((size_t)nwin * B.n >= (size_t(1) << 31)) return fail_arg(ctx, "precompute_bases: windows * n must be < 2^31");
     affine_t *table = nullptr;

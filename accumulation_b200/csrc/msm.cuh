@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
     hist += (size_t)job * sh.sets_per_job * sh.nb;
     const uint32_t half = 1u << (sh.c - 1);
     const unsigned am = __activemask();            // lanes with i < n (the others have returned)
-    const uint32_t lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t carry = 0;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t raw = extract_bits(s.l, w * sh.c, sh.c) + carry;
@@ -191,16 +191,12 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
         }
         digits[(size_t)w * sh.n + i] = enc;
         uint32_t mag = enc & 0x7fffffffu;
-        // Histogram update.  When every lane of the warp lands in the same bucket (constant scalar vectors: the
-        // reference's own fixtures, src/hp_as/mod.rs:991) one lane adds the warp's count instead of 32 lanes
-        // serialising on one L2 address.
+        // Histogram update, aggregated per warp: lanes that land in the same bucket (constant scalar vectors -- the
+        // reference's own fixtures, src/hp_as/mod.rs:991 -- or the short top window, where all n digits fall into a
+        // handful of buckets) send ONE atomic with their count instead of serialising on one L2 address.
         const uint32_t key = mag ? w * sh.hist_stride + mag - 1 : NONE_ID;
-        const uint32_t key0 = __shfl_sync(am, key, leader);
-        if (__all_sync(am, key == key0)) {
-            if (mag && lane == leader) atomicAdd(&hist[key], (uint32_t)__popc(am));
-        } else if (mag) {
-            atomicAdd(&hist[key], 1u);
-        }
+        const unsigned peers = __match_any_sync(am, key);      // lanes of this warp that hit the same bucket
+        if (mag && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
     }
 }
 
@@ -298,20 +294,16 @@ __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__
     cursor += (size_t)job * sh.sets_per_job * sh.nb;
     const uint32_t base_index = msm_base_index(sh, job, i);
     const unsigned am = __activemask();
-    const uint32_t lane = threadIdx.x & 31, leader = __ffs(am) - 1;
-    const uint32_t rank = __popc(am & ((1u << lane) - 1u));
+    const uint32_t lane = threadIdx.x & 31;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t enc = digits[(size_t)w * sh.n + i];
         uint32_t mag = enc & 0x7fffffffu;
         const uint32_t key = mag ? w * sh.hist_stride + mag - 1 : NONE_ID;
-        const uint32_t key0 = __shfl_sync(am, key, leader);
+        const unsigned peers = __match_any_sync(am, key);      // one atomic reserves the range of all lanes in a bucket
+        const uint32_t lead = __ffs(peers) - 1;
         uint32_t pos = 0;
-        if (__all_sync(am, key == key0)) {          // warp-uniform bucket: one atomic reserves the warp's range
-            if (mag && lane == leader) pos = atomicAdd(&cursor[key], (uint32_t)__popc(am));
-            pos = __shfl_sync(am, pos, leader) + rank;
-        } else if (mag) {
-            pos = atomicAdd(&cursor[key], 1u);
-        }
+        if (mag && lane == lead) pos = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+        pos = __shfl_sync(am, pos, lead) + __popc(peers & ((1u << lane) - 1u));
         if (mag) entries[pos] = (w * sh.ent_stride + base_index) | (enc & 0x80000000u);
     }
 }

@@ -421,7 +421,8 @@ def measured_traffic(log_n, c, table):
 
 def table_window_bits(n):
     """mirror of the automatic rule in accmsm_precompute_bases (reporting only)"""
-    return min(20, max(8, max(n, 1).bit_length() - 1))
+    lg = max(n, 1).bit_length() - 1
+    return 20 if lg >= 20 else 17 if lg >= 15 else 15 if lg >= 13 else 10
 
 
 def ctx_window_bits(n):

@@ -63,7 +63,7 @@ int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const 
                           size_t n, uint64_t *handle);
 int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle);
 /* Optional, once per key: build the window table 2^(c w) * base_i (w < ceil(256/c), c = window_bits in 4..21,
- * 0 = automatic: log2(n) clamped to 8..20)
+ * 0 = automatic: 10 / 15 / 17 / 20 for keys below 2^13 / 2^15 / 2^20 / from 2^20 points, measured best)
  * next to the key (ceil(256/c) x 64 B per base).  Commitment keys are fixed from trim / index time on
  * (src/ipa_pc_as/mod.rs:507-513, src/hp_as/mod.rs:640-641), so every later MSM on the handle then uses ONE
  * bucket set: one bucket reduction and no window doublings.  Results are identical with or without it. */
