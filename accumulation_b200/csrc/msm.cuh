@@ -3,18 +3,26 @@
 // PedersenCommitment::commit / IpaPC::cm_commit (reference call sites: src/hp_as/mod.rs:196,197,214,377,
 // 910-918; src/r1cs_nark_as/r1cs_nark/mod.rs:216-261,375-407; src/ipa_pc_as/mod.rs:155,454-462,836-845).
 //
+// Two key layouts: a plain key (per-window bucket sets, Horner over windows at the end) and a key with a window table
+// table[w][i] = 2^(c w) P_i built once at registration (k_precompute): all windows then share ONE bucket set, so there
+// is one bucket reduction and no window doublings.  Up to MAX_JOBS MSMs of equal length share one pass ("jobs").
+//
 // Pipeline (all on one stream, no host round trips):
-//   k_digits      scalar -> (optional from-Montgomery) -> signed radix-2^c digits, histogram of bucket keys
-//   k_scan        exclusive prefix sum of the histogram -> bucket offsets + scatter cursors
-//   k_scatter     counting-sort scatter of (point index | sign) into bucket order
+//   k_digits      scalar source (HBM scalars, h(X) coefficients or IPA round scalars generated in registers) ->
+//                 (optional from-Montgomery) -> signed radix-2^c digits, histogram of bucket keys (atomics
+//                 aggregated per warp with match_any)
+//   k_scan*       exclusive prefix sum of the histogram -> bucket offsets + scatter cursors (tiled beyond 32 K keys)
+//   k_scatter     counting-sort scatter of (table index | sign) into bucket order
 //   k_accumulate  perfectly balanced segmented accumulation: every thread sums an equal-length slice of
 //                 the sorted entry list with XYZZ mixed additions; runs that straddle thread / CTA
 //                 boundaries are merged by a segmented scan in shared memory (hot buckets are
 //                 tree-reduced, never serialised: constant scalar vectors cost the same as random ones)
 //   k_fixup       merges the two boundary partials of every CTA
+//   k_accumulate_warp   short MSMs instead: one warp per bucket, no merging
 //   k_sums /      bucket reduction sum_b b*B_b organised for depth: row / column sums of the bucket index (twice),
 //   k_wsum_leaf   then four 32-item weighted sums, one warp each
-//   k_finish      Horner combine of the window sums (c doublings per window), optional normalisation
+//   k_finish      (plain key: Horner combine of the window sums, c doublings per window), extra partials,
+//                 normalisation with a binary-GCD inversion
 #pragma once
 #include <cuda_runtime.h>
 #include "ec.cuh"
