@@ -15,7 +15,7 @@ SOURCES = ["accmsm.cu"]
 DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc"))) + [os.path.join("..", "..", "include", "accmsm.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-diag-suppress", "550",
 ]
 
 

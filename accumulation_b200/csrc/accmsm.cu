@@ -79,6 +79,11 @@ struct accmsm_ctx {
     affine_t *d_out_affine = nullptr;
     uint32_t *d_out_inf = nullptr;
     uint64_t *h_out = nullptr;   // pinned: 8 u64 affine + 1 u64 inf + 16 u64 partial
+    void *h_stage = nullptr;     // pinned staging for pageable host sources (upload())
+    size_t stage_cap = 0;
+    cudaEvent_t stage_done = nullptr;
+    bool stage_busy = false;
+    std::vector<cudaEvent_t> chunk_events;   // download(): one per staged chunk
     cudaEvent_t ev[ST_COUNT + 1];
     bool ev_valid[ST_COUNT + 1];
     float timings[ST_COUNT];
@@ -325,6 +330,92 @@ int msm_mem1(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uin
     return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st);
 }
 
+// Host -> device copy of a scalar / vector buffer.  Page-locked sources go straight to the DMA engine.  Pageable ones
+// (a Rust Vec, a numpy array) would be staged by the driver on one thread at ~16 GB/s; here they are copied into a
+// page-locked staging buffer by several threads, chunk by chunk, and every chunk's DMA overlaps the next chunk's memcpy.
+int upload(accmsm_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return ACCMSM_OK;
+    constexpr size_t CHUNK = 4u << 20;
+    bool pageable = false;
+    if (bytes >= 2 * CHUNK) {
+        cudaPointerAttributes attr;
+        cudaError_t e = cudaPointerGetAttributes(&attr, h_src);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); pageable = true; }
+        else pageable = attr.type == cudaMemoryTypeUnregistered;
+    }
+    if (!pageable) { CU(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st)); return ACCMSM_OK; }
+    // one staging buffer: wait until the DMA of the previous upload has drained it
+    if (ctx->stage_busy) { CU(ctx, cudaEventSynchronize(ctx->stage_done)); ctx->stage_busy = false; }
+    if (ctx->stage_cap < bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->stage_cap = 0;
+        CU(ctx, cudaMallocHost(&ctx->h_stage, bytes + bytes / 8));
+        ctx->stage_cap = bytes + bytes / 8;
+    }
+    const char *src = (const char *)h_src;
+    char *stage = (char *)ctx->h_stage;
+    for (size_t off = 0; off < bytes; off += CHUNK) {
+        const size_t len = std::min(CHUNK, bytes - off);
+        const int parts = 4;
+#pragma omp parallel for num_threads(parts) schedule(static)
+        for (int p = 0; p < parts; p++) {
+            size_t lo = len * p / parts, hi = len * (p + 1) / parts;
+            memcpy(stage + off + lo, src + off + lo, hi - lo);
+        }
+        CU(ctx, cudaMemcpyAsync((char *)d_dst + off, stage + off, len, cudaMemcpyHostToDevice, st));
+    }
+    CU(ctx, cudaEventRecord(ctx->stage_done, st));
+    ctx->stage_busy = true;
+    return ACCMSM_OK;
+}
+
+// Device -> host copy of a result vector, the mirror image of upload(): for a large pageable destination every chunk is
+// DMA'd into the page-locked staging buffer and copied out by several threads while the next chunks are in flight.
+// Blocks until the data is in h_dst when it takes the staged path; otherwise only enqueues.
+int download(accmsm_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return ACCMSM_OK;
+    constexpr size_t CHUNK = 4u << 20;
+    bool pageable = false;
+    if (bytes >= 2 * CHUNK) {
+        cudaPointerAttributes attr;
+        cudaError_t e = cudaPointerGetAttributes(&attr, h_dst);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); pageable = true; }
+        else pageable = attr.type == cudaMemoryTypeUnregistered;
+    }
+    if (!pageable) { CU(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st)); return ACCMSM_OK; }
+    if (ctx->stage_busy) { CU(ctx, cudaEventSynchronize(ctx->stage_done)); ctx->stage_busy = false; }
+    if (ctx->stage_cap < bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->stage_cap = 0;
+        CU(ctx, cudaMallocHost(&ctx->h_stage, bytes + bytes / 8));
+        ctx->stage_cap = bytes + bytes / 8;
+    }
+    const size_t nchunks = (bytes + CHUNK - 1) / CHUNK;
+    while (ctx->chunk_events.size() < nchunks) {
+        cudaEvent_t ev;
+        CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(ev);
+    }
+    char *dst = (char *)h_dst;
+    const char *stage = (const char *)ctx->h_stage;
+    for (size_t k = 0; k < nchunks; k++) {
+        const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
+        CU(ctx, cudaMemcpyAsync((char *)ctx->h_stage + off, (const char *)d_src + off, len, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaEventRecord(ctx->chunk_events[k], st));
+    }
+    for (size_t k = 0; k < nchunks; k++) {
+        const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
+        CU(ctx, cudaEventSynchronize(ctx->chunk_events[k]));
+        const int parts = 4;
+#pragma omp parallel for num_threads(parts) schedule(static)
+        for (int p = 0; p < parts; p++) {
+            size_t lo = len * p / parts, hi = len * (p + 1) / parts;
+            memcpy(dst + off + lo, stage + off + lo, hi - lo);
+        }
+    }
+    return ACCMSM_OK;
+}
+
 // normalised result -> host
 int fetch_affine(accmsm_ctx *ctx, uint64_t out_xy[8], uint8_t *out_inf, cudaStream_t st) {
     mark(ctx, ST_D2H, st);
@@ -361,7 +452,7 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
     clear_marks(ctx);
     CU(ctx, ctx->scalars.ensure(n * 32));
     mark(ctx, ST_H2D, st);
-    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    { int urc = upload(ctx, ctx->scalars.p, scalars, n * 32, st); if (urc) return urc; }
     int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, nullptr, true, st);
     if (rc) return rc;
     return fetch_affine(ctx, out_xy, out_inf, st);
@@ -402,6 +493,7 @@ int accmsm_init(accmsm_ctx **out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
     for (int i = 0; i <= ST_COUNT; i++) { cudaEventCreate(&ctx->ev[i]); ctx->ev_valid[i] = false; }
+    cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming);
     bool ok = cudaMalloc(&ctx->d_out_affine, MAX_JOBS * sizeof(affine_t)) == cudaSuccess &&
               cudaMalloc(&ctx->d_out_inf, MAX_JOBS * sizeof(uint32_t)) == cudaSuccess &&
               cudaMallocHost(&ctx->h_out, (MAX_JOBS * 9 + 32) * sizeof(uint64_t)) == cudaSuccess;
@@ -451,6 +543,9 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
     if (ctx->d_out_inf) cudaFree(ctx->d_out_inf);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);
+    for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -492,7 +587,7 @@ int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const 
     Bases B;
     B.curve = curve; B.n = n;
     CU(ctx, cudaMalloc(&B.d_xy, std::max<size_t>(n, 1) * sizeof(affine_t)));
-    if (n) CU(ctx, cudaMemcpyAsync(B.d_xy, xy, n * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) { int urc = upload(ctx, B.d_xy, xy, n * sizeof(affine_t), ctx->stream); if (urc) { cudaFree(B.d_xy); return urc; } }
     bool any_inf = false;
     if (infinity) for (size_t i = 0; i < n && !any_inf; i++) any_inf = infinity[i] != 0;
     if (any_inf) {
@@ -566,7 +661,7 @@ int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_
     if (!B) return ACCMSM_E_HANDLE;
     if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "download_bases: range exceeds registered bases");
     CU(ctx, cudaSetDevice(ctx->device));
-    if (n) CU(ctx, cudaMemcpyAsync(xy_out, B->d_xy + offset, n * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) { int drc = download(ctx, xy_out, B->d_xy + offset, n * sizeof(affine_t), ctx->stream); if (drc) return drc; }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return ACCMSM_OK;
 }
@@ -643,7 +738,7 @@ int accmsm_msm_batch(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, 
     clear_marks(ctx);
     CU(ctx, ctx->scalars.ensure(n * k * 32));
     mark(ctx, ST_H2D, st);
-    CU(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * k * 32, cudaMemcpyHostToDevice, st));
+    { int urc = upload(ctx, ctx->scalars.p, scalars, n * k * 32, st); if (urc) return urc; }
     for (size_t j0 = 0; j0 < k; j0 += MAX_JOBS) {
         MsmJobs jobs;
         jobs.njobs = (uint32_t)std::min<size_t>(MAX_JOBS, k - j0);
@@ -678,7 +773,7 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
     clear_marks(ctx);
     CU(ctx, ctx->scalars.ensure((n + 1) * 32));
     mark(ctx, ST_H2D, st);
-    if (n) CU(ctx, cudaMemcpyAsync(ctx->scalars.p, elems_mont, n * 32, cudaMemcpyHostToDevice, st));
+    if (n) { int urc = upload(ctx, ctx->scalars.p, elems_mont, n * 32, st); if (urc) return urc; }
     CU(ctx, cudaMemcpyAsync(ctx->scalars.p + n * 32, randomizer_mont, 32, cudaMemcpyHostToDevice, st));
     MsmJobs jobs(0);
     jobs.tail_base = (uint32_t)hiding_index;
