@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include "../../accumulation_b200/host/ark_mirror.hpp"
 #include "../../oracle/oracle.h"
 
@@ -142,6 +143,22 @@ int main() {
         bool fc_ok = true;
         for (int m = 0; m < 3; m++) fc_ok = fc_ok && fused.first[m] == mv_exp[m] && fused.second[m] == oracle_commit_(curve, gens, mv_exp[m], &hgen, &blinders[m]);
         CHECK((tag + "nark: mat-vec + commitments on the device").c_str(), fc_ok);
+    }
+    // threading: every export is blocking and the ctx serialises its calls, so callers on several host
+    // threads (rayon workers in the reference's deployment) may share one context
+    {
+        const size_t L = 3000;
+        auto pts = gen_points(0, 77, L);
+        CommitterKey ck(ctx, 0, pts);
+        std::vector<std::vector<Fe>> in(4);
+        std::vector<Affine> got(4), exp(4);
+        for (int t = 0; t < 4; t++) { in[t] = gen_scalars(1, 100 + t, L - 10 * t); exp[t] = oracle_commit_(0, std::vector<Affine>(pts.begin(), pts.begin() + (L - 10 * t)), in[t]); }
+        std::vector<std::thread> th;
+        for (int t = 0; t < 4; t++) th.emplace_back([&, t] { for (int r = 0; r < 5; r++) got[t] = PedersenCommitment::commit(ck, in[t]); });
+        for (auto &x : th) x.join();
+        bool ok = true;
+        for (int t = 0; t < 4; t++) ok = ok && got[t] == exp[t];
+        CHECK("four host threads sharing one context", ok);
     }
     // error behaviour: failures surface as exceptions, never as wrong answers
     try {

@@ -19,7 +19,7 @@ def build_harness():
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         lib_dirs = [os.path.join(ROOT, "accumulation_b200"), os.path.join(ROOT, "oracle")]
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", EXE, SRC, f"-L{lib_dirs[0]}", f"-L{lib_dirs[1]}", "-l:libaccmsm.so",
-               "-l:liboracle.so", f"-Wl,-rpath,{lib_dirs[0]}", f"-Wl,-rpath,{lib_dirs[1]}", "-fopenmp"]
+               "-l:liboracle.so", f"-Wl,-rpath,{lib_dirs[0]}", f"-Wl,-rpath,{lib_dirs[1]}", "-fopenmp", "-pthread"]
         subprocess.check_call(cmd)
     return EXE
 
