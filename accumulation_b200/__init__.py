@@ -221,12 +221,18 @@ class Context:
                                                                C.c_void_p(stream)), "ipa_final_key_partial_dev")
 
     # ---- IPA opening session
-    def ipa_open_begin(self, bases: "Bases", coeffs_mont, k: int, point_mont, h_prime_xy) -> int:
+    def ipa_open_begin(self, bases: "Bases", coeffs_mont, k: int, point_mont, h_prime_xy=None) -> int:
+        """h_prime_xy None: follow with ipa_open_use_hiding_generator(session, h_index, xi_0)"""
         cf = _u64(coeffs_mont).reshape(-1, 4)
         sess = C.c_uint64(0)
+        hp = None if h_prime_xy is None else _u64(h_prime_xy)
         self._check(self._lib.accmsm_ipa_open_begin(self._h, C.c_uint64(bases.handle), _p(cf), C.c_size_t(cf.shape[0]), C.c_int(k),
-                                                    _p(_u64(point_mont)), _p(_u64(h_prime_xy)), C.byref(sess)), "ipa_open_begin")
+                                                    _p(_u64(point_mont)), _p(hp), C.byref(sess)), "ipa_open_begin")
         return int(sess.value)
+
+    def ipa_open_use_hiding_generator(self, session: int, h_index: int, xi0_mont):
+        self._check(self._lib.accmsm_ipa_open_use_hiding_generator(self._h, C.c_uint64(session), C.c_size_t(h_index), _p(_u64(xi0_mont))),
+                    "ipa_open_use_hiding_generator")
 
     def ipa_open_begin_combined(self, bases: "Bases", challenges_mont, alphas_mont, point_mont, h_prime_xy, random_poly_mont=None):
         """-> (session, P(point)) with P = [random poly] + sum_j alpha_j h_j(X) built on the device"""
@@ -235,9 +241,10 @@ class Context:
         rp = None if random_poly_mont is None else _u64(random_poly_mont).reshape(-1, 4)
         sess = C.c_uint64(0)
         ev = np.empty(4, dtype=np.uint64)
+        hp = None if h_prime_xy is None else _u64(h_prime_xy)
         self._check(self._lib.accmsm_ipa_open_begin_combined(self._h, C.c_uint64(bases.handle), _p(ch), C.c_int(m), C.c_int(k),
                                                              _p(_u64(alphas_mont)), _p(rp), C.c_size_t(0 if rp is None else rp.shape[0]),
-                                                             _p(_u64(point_mont)), _p(_u64(h_prime_xy)), C.byref(sess), _p(ev)),
+                                                             _p(_u64(point_mont)), _p(hp), C.byref(sess), _p(ev)),
                     "ipa_open_begin_combined")
         return int(sess.value), ev
 

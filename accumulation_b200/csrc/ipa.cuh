@@ -41,17 +41,21 @@ __global__ void __launch_bounds__(256) k_ipa_inner_partial(const uint8_t *__rest
     fe_t s = block_sum<FIELD>(acc, sh);
     if (threadIdx.x == 0) store_fe(partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32, s);
 }
-// grid = 2 blocks: out[y] = canonical(sum of partials[y][0..nparts))  -- canonical because it feeds the bit loop below
+// grid = 2 blocks: out[y] = canonical(scale * sum of partials[y][0..nparts)), scale = 1 when nullptr  -- canonical
+// because it feeds either the byte loop of k_ipa_hp_mul or the digit decomposition of the MSM
 template <int FIELD>
 __global__ void __launch_bounds__(256) k_ipa_inner_final(const uint8_t *__restrict__ partials, uint32_t nparts,
-                                                          uint8_t *__restrict__ out_canon) {
+                                                          const uint8_t *__restrict__ scale, uint8_t *__restrict__ out_canon) {
     using F = Fp<FIELD>;
     __shared__ fe_t sh[256];
     fe_t acc = F::zero();
     for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x)
         acc = F::add(acc, load_fe(partials + ((size_t)blockIdx.x * nparts + i) * 32));
     fe_t s = block_sum<FIELD>(acc, sh);
-    if (threadIdx.x == 0) store_fe(out_canon + (size_t)blockIdx.x * 32, F::from_mont(s));
+    if (threadIdx.x == 0) {
+        if (scale) s = F::mul(s, load_fe(scale));
+        store_fe(out_canon + (size_t)blockIdx.x * 32, F::from_mont(s));
+    }
 }
 
 // hp_table[j] = 2^(8 j) h' (XYZZ), j < 32: one thread, once per opening session

@@ -149,8 +149,11 @@ template <int SFIELD> struct IpaRoundScalars {
     const uint8_t *challenges;  // xi_1 .. xi_j, Montgomery
     int j;
     uint32_t log_h;
+    const uint8_t *tail;        // nullable: 2 canonical scalars, the last pair (hiding generator) of job 0 / job 1
+    uint32_t n_pairs;
     ACC_D fe_t canonical(uint32_t job, uint32_t i) const {
         using F = Fp<SFIELD>;
+        if (tail && i == n_pairs - 1) return load_fe(tail + (size_t)job * 32);
         const uint32_t h = 1u << log_h, ip = i & (h - 1u), u = i >> log_h;
         fe_t acc = load_fe(a + (size_t)((job == 0 ? h : 0u) + ip) * 32);
         for (int m = 1; m <= j; m++) {

@@ -86,9 +86,10 @@ class InnerProductArgPC:
     """The parts of ark_poly_commit::ipa_pc::InnerProductArgPC that run the MSM."""
 
     @staticmethod
-    def open(ck: CommitterKey, combined_coeffs, point, h_prime_xy, round_challenge, log_d: Optional[int] = None):
+    def open(ck: CommitterKey, combined_coeffs, point, h_prime_xy, round_challenge, log_d: Optional[int] = None, xi0=None):
         """Core of open_individual_opening_challenges (src/ipa_pc_as/mod.rs:454-462) after the
-        host has combined the polynomials and derived h' = xi_0 * h.  `round_challenge(prev_xi, l, r) -> xi` is the
+        host has combined the polynomials and derived h' = xi_0 * h (pass either the point h_prime_xy, or xi0 when h is the
+        hiding generator of `ck`: faster, no separate scalar multiplication).  `round_challenge(prev_xi, l, r) -> xi` is the
         host sponge (Montgomery limbs in and out; prev_xi is None in the first round).
         Returns (l_vec, r_vec, final_comm_key_xy, c, challenges)."""
         from . import scalar_field
@@ -96,7 +97,11 @@ class InnerProductArgPC:
         field = scalar_field(ck.curve)
         cf = np.ascontiguousarray(combined_coeffs, dtype=np.uint64).reshape(-1, 4)
         k = log_d if log_d is not None else max(cf.shape[0] - 1, 0).bit_length()
-        sess = ctx.ipa_open_begin(ck.bases, cf, k, point, h_prime_xy)
+        if xi0 is not None:      # h' = xi_0 * (hiding generator registered after the generators): no point needed
+            sess = ctx.ipa_open_begin(ck.bases, cf, k, point, None)
+            ctx.ipa_open_use_hiding_generator(sess, ck.num_generators, xi0)
+        else:
+            sess = ctx.ipa_open_begin(ck.bases, cf, k, point, h_prime_xy)
         l_vec, r_vec, challenges, xi = [], [], [], None
         for _ in range(k):
             l, r = ctx.ipa_open_round(sess)

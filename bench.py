@@ -322,13 +322,13 @@ def main():
             n = 1 << k
             ck = CommitterKey(key, n)
             coeffs = rand_scalars(n, SEED + 99)
-            hp = ctx.download_bases(key, n, 1).reshape(8)
+            xi0 = rand_scalars(1, SEED + 97).reshape(4)               # h' = xi_0 * h with h = base n of the key
             z = rand_scalars(1, SEED + 98).reshape(4)
             ts = []
             for _ in range(2):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                l_vec, r_vec, fk, c, chs = InnerProductArgPC.open(ck, coeffs, z, hp, squeeze, log_d=k)
+                l_vec, r_vec, fk, c, chs = InnerProductArgPC.open(ck, coeffs, z, None, squeeze, log_d=k, xi0=xi0)
                 ts.append((time.perf_counter() - t0) * 1e3)
             ok, _, _ = ctx.ipa_check_final_key(key, np.array(chs), fk, 0)     # the proof's final key passes the decider
             assert ok

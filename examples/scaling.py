@@ -55,7 +55,10 @@ for k in range(args.log_min, args.log_max + 1):
         z = cref.gen_scalars(sf, 100 + k, 1, True).reshape(4)
         hp = ctx.download_bases(bases, n, 1).reshape(8)
         rec["commit_ms"], comm = timed(lambda: InnerProductArgPC.cm_commit(ck, coeffs))
-        rec["open_ms"], proof = timed(lambda: InnerProductArgPC.open(ck, coeffs, z, hp, squeeze, log_d=k), reps=2)
+        xi0 = cref.gen_scalars(sf, 200 + k, 1, True).reshape(4)
+        hgen = hp                                                     # the key's hiding generator (base n)
+        hp, _ = cref.point_mul(curve, hgen, 0, cref.from_mont(sf, xi0.reshape(1, 4)).reshape(4))   # h' = xi_0 * h (host, like upstream)
+        rec["open_ms"], proof = timed(lambda: InnerProductArgPC.open(ck, coeffs, z, None, squeeze, log_d=k, xi0=xi0), reps=2)
         l_vec, r_vec, fk, c, chs = proof
         rec["check_final_key_ms"], ok = timed(lambda: InnerProductArgPC.check_final_key(ck, np.array(chs), fk, 0))
         rec["accept"] = bool(ok)

@@ -156,6 +156,11 @@ int accmsm_ipa_open_begin_combined(accmsm_ctx *ctx, uint64_t handle, const uint6
                                    const uint64_t *alphas_mont, const uint64_t *random_poly_mont, size_t n_random,
                                    const uint64_t point_mont[4], const uint64_t h_prime_xy[8], uint64_t *session,
                                    uint64_t eval_out[4]);
+/* Faster alternative to passing h' as a point: when the hiding generator h is itself a base of the registered key
+ * (index h_index) the host passes xi_0 instead (upstream computes h' = ck.h.mul(xi_0)); <., .> h' then rides in each
+ * round's MSM as the pair (h, <., .> xi_0) and no separate scalar multiplication happens.  Call after begin (where
+ * h_prime_xy may then be NULL) and before the first round. */
+int accmsm_ipa_open_use_hiding_generator(accmsm_ctx *ctx, uint64_t session, size_t h_index, const uint64_t xi0_mont[4]);
 int accmsm_ipa_open_round(accmsm_ctx *ctx, uint64_t session, uint64_t l_xy[8], uint8_t *l_inf,
                           uint64_t r_xy[8], uint8_t *r_inf);
 int accmsm_ipa_open_fold(accmsm_ctx *ctx, uint64_t session, const uint64_t xi_mont[4], const uint64_t xi_inv_mont[4]);

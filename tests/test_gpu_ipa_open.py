@@ -98,3 +98,29 @@ def test_ipa_open_vs_oracle_and_verifies(ctx, curve, k, precompute):
         bad = fk.copy(); bad[3] ^= np.uint64(2)
         assert not ab.InnerProductArgPC.check_final_key(ck, xs, bad, 0)
     ck.bases.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("k", [1, 6, 11])
+def test_ipa_open_with_indexed_hiding_generator(ctx, curve, k):
+    """h' = xi_0 * h with h the hiding generator of the key: passing (index, xi_0) instead of the point gives the same
+    (l, r), final key and c bit for bit (the inner-product term rides in the round MSM as one more pair)."""
+    sf = cref.scalar_field(curve)
+    n = 1 << k
+    pts = cref.gen_points(curve, 60 + k, n + 1)
+    key, h = pts[:n], pts[n]
+    xi0 = cref.gen_scalars(sf, 61, 1, True).reshape(4)
+    hp, hp_inf = cref.point_mul(curve, h, 0, cref.from_mont(sf, xi0.reshape(1, 4)).reshape(4))
+    assert hp_inf == 0
+    coeffs = cref.gen_scalars(sf, 62 + k, n, True)
+    z = cref.gen_scalars(sf, 63, 1, True).reshape(4)
+    squeeze = sponge_stand_in(sf)
+    ck = ab.CommitterKey.new(ctx, curve, key, h, precompute=(k != 6))
+    a = ab.InnerProductArgPC.open(ck, coeffs, z, hp, squeeze, log_d=k)
+    b = ab.InnerProductArgPC.open(ck, coeffs, z, None, squeeze, log_d=k, xi0=xi0)
+    for x, y in zip(a[0] + a[1], b[0] + b[1]):
+        assert same_point(x, y)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    el, er, efk, ec, _ = oracle_open(curve, key, coeffs, z, hp, squeeze)
+    assert all(same_point(x, y) for x, y in zip(b[0] + b[1], el + er)) and np.array_equal(b[2], efk) and np.array_equal(b[3], ec)
+    ck.bases.release()
