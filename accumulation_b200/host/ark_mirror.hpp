@@ -167,12 +167,16 @@ struct InnerProductArgPC {
     }
     // the opening loop of open_individual_opening_challenges (src/ipa_pc_as/mod.rs:454-462); the caller is the host
     // transcript: round_challenge(l, r) -> (xi, xi^-1)
+    // h' = xi_0 * h: pass the point h_prime, or (faster) xi_0 when h is the hiding generator registered with `ck`
     static IpaProofCore open(const CommitterKey &ck, const std::vector<Fe> &combined_coeffs, int log_d, const Fe &point,
-                             const Affine &h_prime, const std::function<std::pair<Fe, Fe>(const Affine &, const Affine &)> &round_challenge) {
+                             const Affine &h_prime, const std::function<std::pair<Fe, Fe>(const Affine &, const Affine &)> &round_challenge,
+                             const std::optional<Fe> &xi0 = std::nullopt) {
         uint64_t hp[8]; affine_to(h_prime, hp);
         uint64_t sess = 0;
+        if (xi0 && !ck.has_hiding()) throw AccmsmError("open: the key has no hiding generator");
         ck.ctx()->check(accmsm_ipa_open_begin(ck.ctx()->raw(), ck.handle(), combined_coeffs.empty() ? nullptr : combined_coeffs[0].data(),
-                                              combined_coeffs.size(), log_d, point.data(), hp, &sess), "ipa_open_begin");
+                                              combined_coeffs.size(), log_d, point.data(), xi0 ? nullptr : hp, &sess), "ipa_open_begin");
+        if (xi0) ck.ctx()->check(accmsm_ipa_open_use_hiding_generator(ck.ctx()->raw(), sess, ck.hiding_index(), xi0->data()), "ipa_open_use_hiding_generator");
         IpaProofCore p;
         for (int r = 0; r < log_d; r++) {
             uint64_t l[8], rr[8]; uint8_t li = 0, ri = 0;

@@ -92,7 +92,7 @@ int main() {
         // --- IpaPC: open (k = 8), succinct-check equation, decider's final-key check
         const int k = 8; const size_t D = size_t(1) << k;
         std::vector<Affine> key(gens.begin(), gens.begin() + D);
-        CommitterKey ipa_ck(ctx, curve, key);
+        CommitterKey ipa_ck(ctx, curve, key, hgen);
         auto coeffs = gen_scalars(sf, 9, D);
         Fe z = gen_scalars(sf, 10, 1)[0];
         auto squeeze = [&](const Affine &l, const Affine &r) {
@@ -107,6 +107,17 @@ int main() {
         CHECK((tag + "ipa open: proof satisfies succinct_check").c_str(),
               oracle_ipa_succinct_check(curve, cx.data(), 0, z.data(), v.data(), lx.data(), rx.data(), k, proof.round_challenges[0].data(), hx.data(),
                                         fx.data(), proof.c.data()) == 1);
+        {   // same opening with h' given as xi_0 * (hiding generator of the key)
+            Fe xi0 = gen_scalars(sf, 15, 1)[0], xi0c;
+            oracle_fe_from_mont(sf, xi0.data(), xi0c.data(), 1);
+            uint64_t hx2[8], hpo[8]; uint8_t hpi = 0; affine_to(hgen, hx2);
+            oracle_point_mul(curve, hx2, 0, xi0c.data(), hpo, &hpi);
+            Affine hprime = affine_from(hpo, hpi);
+            IpaProofCore p1 = InnerProductArgPC::open(ipa_ck, coeffs, k, z, hprime, squeeze);
+            IpaProofCore p2 = InnerProductArgPC::open(ipa_ck, coeffs, k, z, hprime, squeeze, xi0);
+            CHECK((tag + "ipa open: h' as a point == h' as (hiding index, xi_0)").c_str(),
+                  p1.l_vec == p2.l_vec && p1.r_vec == p2.r_vec && p1.final_comm_key == p2.final_comm_key && p1.c == p2.c);
+        }
         SuccinctCheckPolynomial h{proof.round_challenges};
         CHECK((tag + "ipa check: final_comm_key == cm_commit(key, h.compute_coeffs())").c_str(), InnerProductArgPC::check_final_key(ipa_ck, h, proof.final_comm_key));
         Affine bad_key = proof.final_comm_key; bad_key.y[2] ^= 4;
