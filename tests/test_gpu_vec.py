@@ -155,3 +155,20 @@ def test_hp_as_decide_accept_reject(ctx, curve):
             r_bad = (r[0], r[2], r[1])
             assert not ab.ASForHadamardProducts.decide(ck, inst, (a, b, r_bad))
     ck.bases.release()
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_combine_check_polys_edge_shapes(ctx, field):
+    """no h-polynomials at all (only the random linear polynomial), no random polynomial, k = 0"""
+    k = 6
+    rp = cref.gen_scalars(field, 300, 2, True)
+    none = np.zeros((0, k, 4), np.uint64)
+    got = ctx.combine_check_polys(field, none, np.zeros((0, 4), np.uint64), rp)
+    exp = np.zeros((1 << k, 4), np.uint64); exp[:2] = rp
+    assert (got == exp).all()
+    ch = cref.gen_scalars(field, 301, 3 * k, True).reshape(3, k, 4)
+    al = cref.gen_scalars(field, 302, 3, True)
+    assert (ctx.combine_check_polys(field, ch, al) == cref.combine_check_polys(field, ch, al)).all()
+    ch0 = np.zeros((2, 0, 4), np.uint64)
+    al2 = cref.gen_scalars(field, 303, 2, True)
+    assert (ctx.combine_check_polys(field, ch0, al2) == cref.combine_check_polys(field, ch0, al2)).all()   # k = 0: alpha_1 + alpha_2
