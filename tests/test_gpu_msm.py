@@ -397,3 +397,39 @@ def test_error_codes_never_abort(ctx, keys):
         ctx.msm(B, sc, offset=B.n)
     # the context still works afterwards
     assert same_point(ctx.msm(B, sc), cref.commit(0, pts[:10], sc))
+
+
+def test_randomised_shapes_stress(ctx):
+    """seeded sweep over random (curve, key size, table or not, offset, length, scalar form, distribution): every result
+    bit-exact with the oracle.  Exercises the size-dependent dispatch (warp-per-bucket vs balanced accumulation, tiled
+    scan, one- / two-level reduction, window rule) at sizes no other test names explicitly."""
+    rng = np.random.default_rng(0xACC)
+    for trial in range(40):
+        curve = int(rng.integers(0, 2))
+        sf = cref.scalar_field(curve)
+        N = int(2 ** rng.uniform(1, 15.5))
+        pts = cref.gen_points(curve, 5000 + trial, N)
+        B = ctx.register_bases(curve, pts)
+        mode = int(rng.integers(0, 3))
+        if mode == 1:
+            B.precompute()
+        elif mode == 2:
+            B.precompute(int(rng.integers(4, 19)))
+        try:
+            for _ in range(3):
+                n = int(rng.integers(1, N + 1))
+                off = int(rng.integers(0, N - n + 1))
+                mont = bool(rng.integers(0, 2))
+                sc = cref.gen_scalars(sf, int(rng.integers(1, 1 << 30)), n, mont)
+                kind = int(rng.integers(0, 4))
+                if kind == 1:
+                    sc[:] = sc[0]
+                elif kind == 2:
+                    sc[rng.integers(0, n, max(n // 3, 1))] = 0
+                elif kind == 3 and not mont:
+                    sc[:, 2:] = 0
+                exp = cref.commit(curve, pts[off:off + n], sc) if mont else cref.msm_ark(curve, pts[off:off + n], sc)
+                got = ctx.msm(B, sc, montgomery=mont, offset=off)
+                assert same_point(got, exp), (trial, curve, N, mode, n, off, mont, kind)
+        finally:
+            B.release()
