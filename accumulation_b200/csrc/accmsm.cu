@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -75,7 +76,9 @@ struct accmsm_ctx {
     DevBuf<uint32_t> digits, hist, offsets, cursor, entries, cta_ids, tile_sums, tile_offs;
     DevBuf<xyzz_t> buckets, red_sum[2], red_wsum[2], cta_parts, partial;
     DevBuf<uint8_t> scalars, misc;
-    DevBuf<affine_t> oneshot_xy;
+    DevBuf<affine_t> oneshot_xy, pair_pts[2];   // pair_pts / pair_off: ping-pong lists of the batch-affine rounds
+    DevBuf<uint32_t> pair_off[2];
+    int affine_rounds_override = -1;            // development knob (ACCMSM_AFFINE_ROUNDS), -1 = automatic
     affine_t *d_out_affine = nullptr;
     uint32_t *d_out_inf = nullptr;
     uint64_t *h_out = nullptr;   // pinned: 8 u64 affine + 1 u64 inf + 16 u64 partial
@@ -186,6 +189,29 @@ MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, 
     return sh;
 }
 
+// How many batch-affine halving rounds precede the XYZZ accumulation (0 = none).
+int affine_rounds(const accmsm_ctx *ctx, const MsmShape &sh, size_t n_entries) {
+    if (ctx->affine_rounds_override >= 0) return ctx->affine_rounds_override;
+    return 0;
+}
+
+// exclusive scan of counts[0..nkeys) into offsets[0..nkeys] (+ optional copy into cursor)
+int launch_scan(accmsm_ctx *ctx, const uint32_t *counts, uint32_t nkeys, uint32_t *offsets, uint32_t *cursor, cudaStream_t st) {
+    uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles <= SCAN_ONE_CTA_TILES) {
+        k_scan<<<1, 1024, 0, st>>>(counts, nkeys, offsets, cursor);
+        ctx->launches++;
+    } else {
+        CU(ctx, ctx->tile_sums.ensure(ntiles));
+        CU(ctx, ctx->tile_offs.ensure(ntiles + 1));
+        k_scan_tile_sums<<<ntiles, 1024, 0, st>>>(counts, nkeys, ctx->tile_sums.p);
+        k_scan<<<1, 1024, 0, st>>>(ctx->tile_sums.p, ntiles, ctx->tile_offs.p, nullptr);
+        k_scan_tiles<<<ntiles, 1024, 0, st>>>(counts, nkeys, ctx->tile_offs.p, offsets, cursor);
+        ctx->launches += 3;
+    }
+    return ACCMSM_OK;
+}
+
 // The MSM pipeline after the digits kernel has been chosen.  Leaves the per-window sums combined into
 // either a device partial (d_partial) or the normalised affine result in ctx->d_out_affine/d_out_inf.
 template <int CURVE, class Src>
@@ -214,20 +240,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
         ctx->launches++;
     }
     mark(ctx, ST_SCAN, st);
-    {
-        uint32_t ntiles = (sh.nkeys + SCAN_TILE - 1) / SCAN_TILE;
-        if (ntiles <= SCAN_ONE_CTA_TILES) {
-            k_scan<<<1, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p);
-            ctx->launches++;
-        } else {
-            CU(ctx, ctx->tile_sums.ensure(ntiles));
-            CU(ctx, ctx->tile_offs.ensure(ntiles + 1));
-            k_scan_tile_sums<<<ntiles, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->tile_sums.p);
-            k_scan<<<1, 1024, 0, st>>>(ctx->tile_sums.p, ntiles, ctx->tile_offs.p, nullptr);
-            k_scan_tiles<<<ntiles, 1024, 0, st>>>(ctx->hist.p, sh.nkeys, ctx->tile_offs.p, ctx->offsets.p, ctx->cursor.p);
-            ctx->launches += 3;
-        }
-    }
+    { int src = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p, st); if (src) return src; }
     mark(ctx, ST_SCATTER, st);
     {
         dim3 blocks((sh.n + 255) / 256, sh.njobs);
@@ -244,15 +257,33 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
     } else {
         // grid: a whole number of resident waves, shrunk for small inputs so every thread still gets a
         // few entries (upper bound n * nwin; the real count is only known on the device)
+        // optional batch-affine pre-reduction (msm.cuh): `rounds` halvings of every bucket's list in affine coordinates
+        const uint32_t *acc_offsets = ctx->offsets.p, *acc_entries = ctx->entries.p;
+        const affine_t *acc_points = points;
+        size_t acc_bound = n_entries;
+        int rounds = affine_rounds(ctx, sh, n_entries);
+        for (int r = 0; r < rounds; r++) {
+            const size_t out_bound = (acc_bound + sh.nkeys) / 2 + 1;
+            CU(ctx, ctx->pair_off[r & 1].ensure(sh.nkeys + 1));
+            CU(ctx, ctx->pair_pts[r & 1].ensure(out_bound));
+            k_pair_counts<<<(sh.nkeys + 255) / 256, 256, 0, st>>>(acc_offsets, sh.nkeys, ctx->hist.p);
+            ctx->launches++;
+            { int src = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->pair_off[r & 1].p, nullptr, st); if (src) return src; }
+            uint32_t pgrid = (uint32_t)((out_bound + (size_t)PAIR_THREADS * PAIR_B - 1) / ((size_t)PAIR_THREADS * PAIR_B));
+            if (r == 0) k_pair_add<CURVE, true><<<pgrid, PAIR_THREADS, 0, st>>>(acc_offsets, ctx->pair_off[0].p, sh.nkeys, ctx->entries.p, points, ctx->pair_pts[0].p);
+            else k_pair_add<CURVE, false><<<pgrid, PAIR_THREADS, 0, st>>>(acc_offsets, ctx->pair_off[r & 1].p, sh.nkeys, nullptr, acc_points, ctx->pair_pts[r & 1].p);
+            ctx->launches++;
+            acc_offsets = ctx->pair_off[r & 1].p; acc_entries = nullptr; acc_points = ctx->pair_pts[r & 1].p; acc_bound = out_bound;
+        }
         int per_sm = ctx->acc_ctas_per_sm[CURVE];
         uint32_t gmax = (uint32_t)(ctx->sm_count * per_sm);
-        uint32_t want = (uint32_t)((n_entries + (size_t)ACC_THREADS * 8 - 1) / ((size_t)ACC_THREADS * 8));
+        uint32_t want = (uint32_t)((acc_bound + (size_t)ACC_THREADS * 8 - 1) / ((size_t)ACC_THREADS * 8));
         uint32_t grid = std::max(1u, std::min(gmax, want));
         CU(ctx, ctx->cta_ids.ensure(2 * grid));
         CU(ctx, ctx->cta_parts.ensure(2 * grid));
         size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
-        k_accumulate<CURVE><<<grid, ACC_THREADS, smem, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p,
-                                                              points, ctx->buckets.p,
+        k_accumulate<CURVE><<<grid, ACC_THREADS, smem, st>>>(acc_offsets, sh.nkeys, acc_entries,
+                                                              acc_points, ctx->buckets.p,
                                                               ctx->cta_ids.p, ctx->cta_parts.p);
         mark(ctx, ST_FIXUP, st);
         uint32_t ns = 2 * grid;
@@ -488,6 +519,7 @@ int accmsm_init(accmsm_ctx **out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) return ACCMSM_E_CUDA;
     accmsm_ctx *ctx = new accmsm_ctx();
     ctx->device = device;
+    if (const char *e = getenv("ACCMSM_AFFINE_ROUNDS")) ctx->affine_rounds_override = atoi(e);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
@@ -539,6 +571,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release();
+    for (int i = 0; i < 2; i++) { ctx->pair_pts[i].release(); ctx->pair_off[i].release(); }
     for (int i = 0; i < 2; i++) { ctx->red_sum[i].release(); ctx->red_wsum[i].release(); }
     if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
     if (ctx->d_out_inf) cudaFree(ctx->d_out_inf);

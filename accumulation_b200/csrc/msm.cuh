@@ -404,7 +404,9 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
         uint32_t k = lo, bend = offsets[k + 1];
         bool first_run = true;
         xyzz_t acc = Cv::identity();
-        uint32_t ent = entries[s];
+        // entries == nullptr: "direct" list (after batch-affine rounds, below): entry p IS point p of `bases`, no sign,
+        // and a point (0, 0) stands for the identity
+        uint32_t ent = entries ? entries[s] : s;
         affine_t pt = load_affine(bases + (ent & 0x7fffffffu));
 #pragma unroll 1
         for (uint32_t p = s; p < e; p++) {
@@ -425,11 +427,11 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
             const uint32_t cur_sign = ent >> 31;
             affine_t cur = pt;
             if (p + 1 < e) {                       // software prefetch of the next point (a gather from HBM / L2)
-                ent = entries[p + 1];
+                ent = entries ? entries[p + 1] : p + 1;
                 pt = load_affine(bases + (ent & 0x7fffffffu));
             }
             if (cur_sign) cur.y = Cv::F::neg(cur.y);
-            Cv::madd(acc, cur);
+            if (entries || !(Cv::F::is_zero(cur.x) && Cv::F::is_zero(cur.y))) Cv::madd(acc, cur);
         }
         if (first_run) { slot_pt[2 * threadIdx.x] = acc; head_id = k; tail_id = k; }   // equal ids stay contiguous
         else { slot_pt[2 * threadIdx.x + 1] = acc; tail_id = k; }
@@ -500,6 +502,184 @@ __global__ void __launch_bounds__(256) k_accumulate_warp(const uint32_t *__restr
         }
     }
     if (lane == 0) store_xyzz(buckets + k, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batch-affine pre-reduction.  One round halves the points of every bucket: neighbours
+// (2j, 2j + 1) of the bucket's list are added in AFFINE coordinates,
+//     lambda = (y1 - y0) / (x1 - x0),  x3 = lambda^2 - x0 - x1,  y3 = lambda (x0 - x3) - y0        (5M + 1S + 1 inversion)
+// and all 256 * PAIR_B divisions of a CTA share ONE inversion (Montgomery's trick: per-thread prefix products, a
+// product scan over the CTA in shared memory, one binary-GCD inversion by thread 0, back-substitution).  That is
+// ~6.6 products per addition instead of the 10 of the XYZZ mixed add.  After a few rounds the shortened lists go
+// through k_accumulate in "direct" mode.  Exceptional pairs are peeled: x0 == x1 with y0 == y1 is a doubling
+// (lambda = 3 x0^2 / 2 y0), with y0 == -y1 the sum is the identity, stored as (0, 0) and skipped downstream; an odd
+// last element or an identity partner passes through.  Results are the same affine points any other addition law gives.
+// ------------------------------------------------------------------------------------------------
+constexpr int PAIR_THREADS = 256;
+constexpr int PAIR_B = 16;              // output slots per thread
+
+__global__ void __launch_bounds__(256) k_pair_counts(const uint32_t *__restrict__ offsets, uint32_t nkeys,
+                                                      uint32_t *__restrict__ counts) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nkeys) counts[k] = (offsets[k + 1] - offsets[k] + 1u) >> 1;
+}
+
+// one input point of a pair round: FIRST round reads the table through the sorted entry list (index | sign)
+template <int CURVE, bool FIRST>
+ACC_D affine_t pair_load(const uint32_t *__restrict__ entries, const affine_t *__restrict__ pts, uint32_t i) {
+    using F = typename Curve<CURVE>::F;
+    if (FIRST) {
+        uint32_t ent = entries[i];
+        affine_t p = load_affine(pts + (ent & 0x7fffffffu));
+        if (ent >> 31) p.y = F::neg(p.y);
+        return p;
+    }
+    return load_affine(pts + i);
+}
+ACC_D bool affine_is_identity_marker(const affine_t &p) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= p.x.l[i] | p.y.l[i];
+    return d == 0;
+}
+
+// kind of a slot: 0 = pass p0 through, 1 = pass p1 through, 2 = generic add, 3 = doubling, 4 = identity
+template <int CURVE>
+ACC_D int pair_classify(const affine_t &p0, const affine_t &p1, bool has_pair, fe_t &den) {
+    using F = typename Curve<CURVE>::F;
+    den = F::one();
+    if (!has_pair) return 0;
+    const bool id0 = affine_is_identity_marker(p0), id1 = affine_is_identity_marker(p1);
+    if (id1) return 0;            // p0 (possibly the marker itself) passes through
+    if (id0) return 1;
+    fe_t dx = F::sub(p1.x, p0.x);
+    if (!F::is_zero(dx)) { den = dx; return 2; }
+    if (F::eq(p0.y, p1.y) && !F::is_zero(p0.y)) { den = F::dbl(p0.y); return 3; }
+    return 4;
+}
+
+template <int CURVE, bool FIRST>
+__global__ void __launch_bounds__(PAIR_THREADS) k_pair_add(const uint32_t *__restrict__ off_in, const uint32_t *__restrict__ off_out,
+                                                           uint32_t nkeys, const uint32_t *__restrict__ entries,
+                                                           const affine_t *__restrict__ pts_in, affine_t *__restrict__ pts_out) {
+    using Cv = Curve<CURVE>;
+    using F = typename Cv::F;
+    __shared__ fe_t sh_pre[PAIR_THREADS];     // inclusive prefix products of the per-thread totals
+    __shared__ fe_t sh_suf[PAIR_THREADS];     // inclusive suffix products
+    __shared__ fe_t sh_inv;
+    const uint32_t M_out = off_out[nkeys];
+    if ((uint64_t)blockIdx.x * PAIR_THREADS * PAIR_B >= M_out) return;      // whole CTA beyond the list (grid is an upper bound)
+    const uint32_t t = blockIdx.x * PAIR_THREADS + threadIdx.x;
+    const uint64_t s64 = (uint64_t)t * PAIR_B;
+    const uint32_t s0 = s64 < M_out ? (uint32_t)s64 : M_out;
+    const uint32_t s1 = (s64 + PAIR_B < M_out) ? (uint32_t)(s64 + PAIR_B) : M_out;
+
+    // bucket of slot s0
+    uint32_t k0 = 0;
+    if (s0 < s1) {
+        uint32_t lo = 0, hi = nkeys - 1;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (off_out[mid + 1] > s0) hi = mid; else lo = mid + 1;
+        }
+        k0 = lo;
+    }
+    // ---- phase A: denominators and per-thread prefix products
+    fe_t pref[PAIR_B];
+    fe_t run = F::one();
+    {
+        uint32_t k = k0, bend = s0 < s1 ? off_out[k + 1] : 0;
+#pragma unroll 1
+        for (uint32_t s = s0; s < s1; s++) {
+            if (s == bend) {
+                k++; bend = off_out[k + 1];
+                if (bend == s) {                   // empty buckets ahead: binary search instead of a linear walk
+                    uint32_t blo = k + 1, bhi = nkeys - 1;
+                    while (blo < bhi) {
+                        uint32_t mid = (blo + bhi) >> 1;
+                        if (off_out[mid + 1] > s) bhi = mid; else blo = mid + 1;
+                    }
+                    k = blo; bend = off_out[k + 1];
+                }
+            }
+            const uint32_t j = s - off_out[k];
+            const uint32_t i0 = off_in[k] + 2 * j;
+            const bool has_pair = i0 + 1 < off_in[k + 1];
+            affine_t p0 = pair_load<CURVE, FIRST>(entries, pts_in, i0);
+            affine_t p1 = has_pair ? pair_load<CURVE, FIRST>(entries, pts_in, i0 + 1) : p0;
+            fe_t den;
+            pair_classify<CURVE>(p0, p1, has_pair, den);
+            pref[s - s0] = run;
+            run = F::mul(run, den);
+        }
+    }
+    // ---- one inversion for the CTA: scans of the per-thread totals, total inverted by thread 0
+    sh_pre[threadIdx.x] = run;
+    sh_suf[threadIdx.x] = run;
+    __syncthreads();
+#pragma unroll 1
+    for (int d = 1; d < PAIR_THREADS; d <<= 1) {
+        fe_t a, b;
+        const bool up = (int)threadIdx.x >= d, dn = (int)threadIdx.x + d < PAIR_THREADS;
+        if (up) a = F::mul(sh_pre[threadIdx.x], sh_pre[threadIdx.x - d]);
+        if (dn) b = F::mul(sh_suf[threadIdx.x], sh_suf[threadIdx.x + d]);
+        __syncthreads();
+        if (up) sh_pre[threadIdx.x] = a;
+        if (dn) sh_suf[threadIdx.x] = b;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sh_inv = F::inv_gcd(sh_pre[PAIR_THREADS - 1]);
+    __syncthreads();
+    // inverse of this thread's own total: inv(total) * (product of the others) = inv(T) * pre[t-1] * suf[t+1]
+    fe_t rinv = sh_inv;
+    if (threadIdx.x > 0) rinv = F::mul(rinv, sh_pre[threadIdx.x - 1]);
+    if (threadIdx.x + 1 < PAIR_THREADS) rinv = F::mul(rinv, sh_suf[threadIdx.x + 1]);
+    // ---- phase B: back-substitution, slopes, sums
+    if (s0 < s1) {
+        // walk the slots backwards; the bucket of s1 - 1 by binary search again
+        uint32_t lo = 0, hi = nkeys - 1;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (off_out[mid + 1] > s1 - 1) hi = mid; else lo = mid + 1;
+        }
+        uint32_t k = lo, bstart = off_out[k];
+#pragma unroll 1
+        for (uint32_t s = s1; s-- > s0;) {
+            if (s < bstart) {
+                k--; bstart = off_out[k];
+                if (s < bstart) {                  // empty buckets behind: binary search for the bucket holding slot s
+                    uint32_t blo = 0, bhi = k;
+                    while (blo < bhi) {
+                        uint32_t mid = (blo + bhi) >> 1;
+                        if (off_out[mid + 1] > s) bhi = mid; else blo = mid + 1;
+                    }
+                    k = blo; bstart = off_out[k];
+                }
+            }
+            const uint32_t j = s - bstart;
+            const uint32_t i0 = off_in[k] + 2 * j;
+            const bool has_pair = i0 + 1 < off_in[k + 1];
+            affine_t p0 = pair_load<CURVE, FIRST>(entries, pts_in, i0);
+            affine_t p1 = has_pair ? pair_load<CURVE, FIRST>(entries, pts_in, i0 + 1) : p0;
+            fe_t den;
+            const int kind = pair_classify<CURVE>(p0, p1, has_pair, den);
+            const fe_t dinv = F::mul(rinv, pref[s - s0]);     // 1 / den of this slot
+            rinv = F::mul(rinv, den);
+            affine_t r;
+            if (kind == 0) r = p0;
+            else if (kind == 1) r = p1;
+            else if (kind == 4) { r.x = F::zero(); r.y = F::zero(); }
+            else {
+                fe_t num;
+                if (kind == 2) num = F::sub(p1.y, p0.y);
+                else { fe_t xx = F::sqr(p0.x); num = F::add(F::dbl(xx), xx); }
+                const fe_t lam = F::mul(num, dinv);
+                r.x = F::sub(F::sub(F::sqr(lam), p0.x), p1.x);
+                r.y = F::sub(F::mul(lam, F::sub(p0.x, r.x)), p0.y);
+            }
+            store_fe(&pts_out[s].x, r.x); store_fe(&pts_out[s].y, r.y);
+        }
+    }
 }
 
 // k_fixup: one CTA merges the 2 * G boundary partials left by k_accumulate and writes the buckets.

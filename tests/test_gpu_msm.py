@@ -433,3 +433,29 @@ def test_randomised_shapes_stress(ctx):
                 assert same_point(got, exp), (trial, curve, N, mode, n, off, mont, kind)
         finally:
             B.release()
+
+
+def test_experimental_batch_affine_rounds(monkeypatch):
+    """the batch-affine pre-reduction (off by default: measured slower than the XYZZ path so far) must
+    still give the same points: shared inversion, doubling / cancelling / pass-through pairs, identity markers"""
+    monkeypatch.setenv("ACCMSM_AFFINE_ROUNDS", "3")
+    c2 = ab.Context(0)
+    try:
+        for curve in (0, 1):
+            sf = cref.scalar_field(curve)
+            n = 20000
+            base = cref.gen_points(curve, 990 + curve, n)
+            bm = pyref.base_modulus(curve)
+            neg = base[:50].copy()
+            y = cref.from_mont(cref.base_field(curve), neg[:, 4:])
+            neg[:, 4:] = cref.to_mont(cref.base_field(curve), cref.ints_to_arr([(bm - v) % bm for v in cref.arr_to_ints(y)]))
+            pts = np.concatenate([base, base[:50], neg, base[:1].repeat(33, axis=0)])      # duplicates and opposite points
+            B = c2.register_bases(curve, pts).precompute(10)
+            N = pts.shape[0]
+            rnd = cref.gen_scalars(sf, 991, N, True)
+            const = np.repeat(rnd[:1], N, axis=0)
+            for sc in (rnd, const):
+                assert same_point(c2.msm(B, sc), cref.commit(curve, pts, sc))
+            B.release()
+    finally:
+        c2.close()
