@@ -78,6 +78,7 @@ struct accmsm_ctx {
     DevBuf<uint8_t> scalars, misc;
     DevBuf<affine_t> oneshot_xy, pair_pts[2];   // pair_pts / pair_off: ping-pong lists of the batch-affine rounds
     DevBuf<uint32_t> pair_off[2];
+    DevBuf<uint8_t> pair_pref, pair_kinds, pair_tfac, pair_ctot, pair_cfac;
     int affine_rounds_override = -1;            // development knob (ACCMSM_AFFINE_ROUNDS), -1 = automatic
     affine_t *d_out_affine = nullptr;
     uint32_t *d_out_inf = nullptr;
@@ -270,9 +271,23 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
             ctx->launches++;
             { int src = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->pair_off[r & 1].p, nullptr, st); if (src) return src; }
             uint32_t pgrid = (uint32_t)((out_bound + (size_t)PAIR_THREADS * PAIR_B - 1) / ((size_t)PAIR_THREADS * PAIR_B));
-            if (r == 0) k_pair_add<CURVE, true><<<pgrid, PAIR_THREADS, 0, st>>>(acc_offsets, ctx->pair_off[0].p, sh.nkeys, ctx->entries.p, points, ctx->pair_pts[0].p);
-            else k_pair_add<CURVE, false><<<pgrid, PAIR_THREADS, 0, st>>>(acc_offsets, ctx->pair_off[r & 1].p, sh.nkeys, nullptr, acc_points, ctx->pair_pts[r & 1].p);
-            ctx->launches++;
+            CU(ctx, ctx->pair_pref.ensure(out_bound * 32));
+            CU(ctx, ctx->pair_kinds.ensure(out_bound));
+            CU(ctx, ctx->pair_tfac.ensure((size_t)pgrid * PAIR_THREADS * 32));
+            CU(ctx, ctx->pair_ctot.ensure((size_t)pgrid * 32));
+            CU(ctx, ctx->pair_cfac.ensure((size_t)pgrid * 32));
+            const uint32_t *oin = acc_offsets, *oout = ctx->pair_off[r & 1].p;
+            affine_t *pout = ctx->pair_pts[r & 1].p;
+            if (r == 0) {
+                k_pair_fwd<CURVE, true><<<pgrid, PAIR_THREADS, 0, st>>>(oin, oout, sh.nkeys, ctx->entries.p, points, ctx->pair_pref.p, ctx->pair_kinds.p, ctx->pair_tfac.p, ctx->pair_ctot.p);
+                k_pair_mid<CURVE><<<1, PAIR_MID_THREADS, 0, st>>>(oout, sh.nkeys, ctx->pair_ctot.p, ctx->pair_cfac.p);
+                k_pair_bwd<CURVE, true><<<pgrid, PAIR_THREADS, 0, st>>>(oin, oout, sh.nkeys, ctx->entries.p, points, ctx->pair_pref.p, ctx->pair_kinds.p, ctx->pair_tfac.p, ctx->pair_cfac.p, pout);
+            } else {
+                k_pair_fwd<CURVE, false><<<pgrid, PAIR_THREADS, 0, st>>>(oin, oout, sh.nkeys, nullptr, acc_points, ctx->pair_pref.p, ctx->pair_kinds.p, ctx->pair_tfac.p, ctx->pair_ctot.p);
+                k_pair_mid<CURVE><<<1, PAIR_MID_THREADS, 0, st>>>(oout, sh.nkeys, ctx->pair_ctot.p, ctx->pair_cfac.p);
+                k_pair_bwd<CURVE, false><<<pgrid, PAIR_THREADS, 0, st>>>(oin, oout, sh.nkeys, nullptr, acc_points, ctx->pair_pref.p, ctx->pair_kinds.p, ctx->pair_tfac.p, ctx->pair_cfac.p, pout);
+            }
+            ctx->launches += 3;
             acc_offsets = ctx->pair_off[r & 1].p; acc_entries = nullptr; acc_points = ctx->pair_pts[r & 1].p; acc_bound = out_bound;
         }
         int per_sm = ctx->acc_ctas_per_sm[CURVE];
@@ -572,6 +587,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release();
     for (int i = 0; i < 2; i++) { ctx->pair_pts[i].release(); ctx->pair_off[i].release(); }
+    ctx->pair_pref.release(); ctx->pair_kinds.release(); ctx->pair_tfac.release(); ctx->pair_ctot.release(); ctx->pair_cfac.release();
     for (int i = 0; i < 2; i++) { ctx->red_sum[i].release(); ctx->red_wsum[i].release(); }
     if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
     if (ctx->d_out_inf) cudaFree(ctx->d_out_inf);

@@ -364,6 +364,19 @@ ACC_D void seg_scan(xyzz_t *pt, const uint32_t *id, uint32_t ns) {
     }
 }
 
+// The identity cannot be an affine record; it is stored as x = 2^256 - 1 (not a canonical field element), y = 0.
+ACC_D bool affine_is_identity_marker(const fe_t &x) {
+    uint32_t d = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d &= x.l[i];
+    return d == 0xffffffffu;
+}
+ACC_D affine_t affine_identity_marker() {
+    affine_t r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { r.x.l[i] = 0xffffffffu; r.y.l[i] = 0u; }
+    return r;
+}
 // ------------------------------------------------------------------------------------------------
 // k_accumulate
 // ------------------------------------------------------------------------------------------------
@@ -405,7 +418,7 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
         bool first_run = true;
         xyzz_t acc = Cv::identity();
         // entries == nullptr: "direct" list (after batch-affine rounds, below): entry p IS point p of `bases`, no sign,
-        // and a point (0, 0) stands for the identity
+        // and x = 2^256 - 1 marks the identity
         uint32_t ent = entries ? entries[s] : s;
         affine_t pt = load_affine(bases + (ent & 0x7fffffffu));
 #pragma unroll 1
@@ -431,7 +444,7 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
                 pt = load_affine(bases + (ent & 0x7fffffffu));
             }
             if (cur_sign) cur.y = Cv::F::neg(cur.y);
-            if (entries || !(Cv::F::is_zero(cur.x) && Cv::F::is_zero(cur.y))) Cv::madd(acc, cur);
+            if (entries || !affine_is_identity_marker(cur.x)) Cv::madd(acc, cur);
         }
         if (first_run) { slot_pt[2 * threadIdx.x] = acc; head_id = k; tail_id = k; }   // equal ids stay contiguous
         else { slot_pt[2 * threadIdx.x + 1] = acc; tail_id = k; }
@@ -508,15 +521,17 @@ __global__ void __launch_bounds__(256) k_accumulate_warp(const uint32_t *__restr
 // Batch-affine pre-reduction.  One round halves the points of every bucket: neighbours
 // (2j, 2j + 1) of the bucket's list are added in AFFINE coordinates,
 //     lambda = (y1 - y0) / (x1 - x0),  x3 = lambda^2 - x0 - x1,  y3 = lambda (x0 - x3) - y0        (5M + 1S + 1 inversion)
-// and all 256 * PAIR_B divisions of a CTA share ONE inversion (Montgomery's trick: per-thread prefix products, a
-// product scan over the CTA in shared memory, one binary-GCD inversion by thread 0, back-substitution).  That is
-// ~6.6 products per addition instead of the 10 of the XYZZ mixed add.  After a few rounds the shortened lists go
-// through k_accumulate in "direct" mode.  Exceptional pairs are peeled: x0 == x1 with y0 == y1 is a doubling
-// (lambda = 3 x0^2 / 2 y0), with y0 == -y1 the sum is the identity, stored as (0, 0) and skipped downstream; an odd
+// and ALL divisions of a round share ONE inversion (Montgomery's trick across the whole grid): k_pair_fwd computes the
+// denominators and per-thread prefix products and scans the thread totals over the CTA, k_pair_mid scans the CTA totals
+// and inverts the grid total once (binary GCD), k_pair_bwd back-substitutes and forms the sums.  That is ~6 products
+// per addition instead of the 10 of the XYZZ mixed add.  After a few rounds the shortened lists go through
+// k_accumulate in "direct" mode.  Exceptional pairs are peeled: x0 == x1 with y0 == y1 is a doubling
+// (lambda = 3 x0^2 / 2 y0), with y0 == -y1 the sum is the identity (stored as a marker, skipped downstream); an odd
 // last element or an identity partner passes through.  Results are the same affine points any other addition law gives.
 // ------------------------------------------------------------------------------------------------
 constexpr int PAIR_THREADS = 256;
-constexpr int PAIR_B = 16;              // output slots per thread
+constexpr int PAIR_B = 32;              // output slots per thread
+constexpr int PAIR_MID_THREADS = 1024;
 
 __global__ void __launch_bounds__(256) k_pair_counts(const uint32_t *__restrict__ offsets, uint32_t nkeys,
                                                       uint32_t *__restrict__ counts) {
@@ -524,96 +539,87 @@ __global__ void __launch_bounds__(256) k_pair_counts(const uint32_t *__restrict_
     if (k < nkeys) counts[k] = (offsets[k + 1] - offsets[k] + 1u) >> 1;
 }
 
-// one input point of a pair round: FIRST round reads the table through the sorted entry list (index | sign)
+// x / y of input i of a pair round: the FIRST round reads the window table through the sorted entry list (index | sign)
+template <bool FIRST>
+ACC_D fe_t pair_load_x(const uint32_t *__restrict__ entries, const affine_t *__restrict__ pts, uint32_t i) {
+    return load_fe_nc(&pts[FIRST ? (entries[i] & 0x7fffffffu) : i].x);
+}
 template <int CURVE, bool FIRST>
-ACC_D affine_t pair_load(const uint32_t *__restrict__ entries, const affine_t *__restrict__ pts, uint32_t i) {
+ACC_D fe_t pair_load_y(const uint32_t *__restrict__ entries, const affine_t *__restrict__ pts, uint32_t i) {
     using F = typename Curve<CURVE>::F;
     if (FIRST) {
         uint32_t ent = entries[i];
-        affine_t p = load_affine(pts + (ent & 0x7fffffffu));
-        if (ent >> 31) p.y = F::neg(p.y);
-        return p;
+        fe_t y = load_fe_nc(&pts[ent & 0x7fffffffu].y);
+        return (ent >> 31) ? F::neg(y) : y;
     }
-    return load_affine(pts + i);
+    return load_fe_nc(&pts[i].y);
 }
-ACC_D bool affine_is_identity_marker(const affine_t &p) {
-    uint32_t d = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) d |= p.x.l[i] | p.y.l[i];
-    return d == 0;
-}
+enum : uint8_t { PAIR_PASS0 = 0, PAIR_PASS1 = 1, PAIR_ADD = 2, PAIR_DBL = 3, PAIR_IDENT = 4 };
 
-// kind of a slot: 0 = pass p0 through, 1 = pass p1 through, 2 = generic add, 3 = doubling, 4 = identity
-template <int CURVE>
-ACC_D int pair_classify(const affine_t &p0, const affine_t &p1, bool has_pair, fe_t &den) {
-    using F = typename Curve<CURVE>::F;
-    den = F::one();
-    if (!has_pair) return 0;
-    const bool id0 = affine_is_identity_marker(p0), id1 = affine_is_identity_marker(p1);
-    if (id1) return 0;            // p0 (possibly the marker itself) passes through
-    if (id0) return 1;
-    fe_t dx = F::sub(p1.x, p0.x);
-    if (!F::is_zero(dx)) { den = dx; return 2; }
-    if (F::eq(p0.y, p1.y) && !F::is_zero(p0.y)) { den = F::dbl(p0.y); return 3; }
-    return 4;
-}
+// walks the output slots [s0, s1) of one thread forwards: bucket k of slot s without a linear walk over empty buckets
+struct PairWalk {
+    uint32_t k, bend;
+    ACC_D void init(const uint32_t *__restrict__ off_out, uint32_t nkeys, uint32_t s) {
+        uint32_t lo = 0, hi = nkeys - 1;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (off_out[mid + 1] > s) hi = mid; else lo = mid + 1;
+        }
+        k = lo; bend = off_out[k + 1];
+    }
+    ACC_D void advance_to(const uint32_t *__restrict__ off_out, uint32_t nkeys, uint32_t s) {
+        if (s != bend) return;
+        k++; bend = off_out[k + 1];
+        if (bend == s) init(off_out, nkeys, s);
+    }
+};
 
+// forward pass: denominators, per-thread prefix products (to HBM), pair kinds; product scans over the CTA; the thread's
+// share of the inverse (everything but the grid-wide inverse) and the CTA total go to HBM
 template <int CURVE, bool FIRST>
-__global__ void __launch_bounds__(PAIR_THREADS) k_pair_add(const uint32_t *__restrict__ off_in, const uint32_t *__restrict__ off_out,
+__global__ void __launch_bounds__(PAIR_THREADS) k_pair_fwd(const uint32_t *__restrict__ off_in, const uint32_t *__restrict__ off_out,
                                                            uint32_t nkeys, const uint32_t *__restrict__ entries,
-                                                           const affine_t *__restrict__ pts_in, affine_t *__restrict__ pts_out) {
-    using Cv = Curve<CURVE>;
-    using F = typename Cv::F;
-    __shared__ fe_t sh_pre[PAIR_THREADS];     // inclusive prefix products of the per-thread totals
-    __shared__ fe_t sh_suf[PAIR_THREADS];     // inclusive suffix products
-    __shared__ fe_t sh_inv;
+                                                           const affine_t *__restrict__ pts_in, uint8_t *__restrict__ pref,
+                                                           uint8_t *__restrict__ kinds, uint8_t *__restrict__ thread_factor,
+                                                           uint8_t *__restrict__ cta_total) {
+    using F = typename Curve<CURVE>::F;
+    __shared__ fe_t sh_pre[PAIR_THREADS];
+    __shared__ fe_t sh_suf[PAIR_THREADS];
     const uint32_t M_out = off_out[nkeys];
     if ((uint64_t)blockIdx.x * PAIR_THREADS * PAIR_B >= M_out) return;      // whole CTA beyond the list (grid is an upper bound)
     const uint32_t t = blockIdx.x * PAIR_THREADS + threadIdx.x;
     const uint64_t s64 = (uint64_t)t * PAIR_B;
     const uint32_t s0 = s64 < M_out ? (uint32_t)s64 : M_out;
     const uint32_t s1 = (s64 + PAIR_B < M_out) ? (uint32_t)(s64 + PAIR_B) : M_out;
-
-    // bucket of slot s0
-    uint32_t k0 = 0;
-    if (s0 < s1) {
-        uint32_t lo = 0, hi = nkeys - 1;
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (off_out[mid + 1] > s0) hi = mid; else lo = mid + 1;
-        }
-        k0 = lo;
-    }
-    // ---- phase A: denominators and per-thread prefix products
-    fe_t pref[PAIR_B];
     fe_t run = F::one();
-    {
-        uint32_t k = k0, bend = s0 < s1 ? off_out[k + 1] : 0;
+    if (s0 < s1) {
+        PairWalk w; w.init(off_out, nkeys, s0);
 #pragma unroll 1
         for (uint32_t s = s0; s < s1; s++) {
-            if (s == bend) {
-                k++; bend = off_out[k + 1];
-                if (bend == s) {                   // empty buckets ahead: binary search instead of a linear walk
-                    uint32_t blo = k + 1, bhi = nkeys - 1;
-                    while (blo < bhi) {
-                        uint32_t mid = (blo + bhi) >> 1;
-                        if (off_out[mid + 1] > s) bhi = mid; else blo = mid + 1;
+            w.advance_to(off_out, nkeys, s);
+            const uint32_t i0 = off_in[w.k] + 2 * (s - off_out[w.k]);
+            const bool has_pair = i0 + 1 < off_in[w.k + 1];
+            uint8_t kind = PAIR_PASS0;
+            fe_t den = F::one();
+            if (has_pair) {
+                const fe_t x0 = pair_load_x<FIRST>(entries, pts_in, i0), x1 = pair_load_x<FIRST>(entries, pts_in, i0 + 1);
+                if (!FIRST && affine_is_identity_marker(x1)) kind = PAIR_PASS0;
+                else if (!FIRST && affine_is_identity_marker(x0)) kind = PAIR_PASS1;
+                else {
+                    den = F::sub(x1, x0);
+                    kind = PAIR_ADD;
+                    if (F::is_zero(den)) {           // same x: doubling or cancellation
+                        const fe_t y0 = pair_load_y<CURVE, FIRST>(entries, pts_in, i0), y1 = pair_load_y<CURVE, FIRST>(entries, pts_in, i0 + 1);
+                        if (F::eq(y0, y1) && !F::is_zero(y0)) { den = F::dbl(y0); kind = PAIR_DBL; }
+                        else { den = F::one(); kind = PAIR_IDENT; }
                     }
-                    k = blo; bend = off_out[k + 1];
                 }
             }
-            const uint32_t j = s - off_out[k];
-            const uint32_t i0 = off_in[k] + 2 * j;
-            const bool has_pair = i0 + 1 < off_in[k + 1];
-            affine_t p0 = pair_load<CURVE, FIRST>(entries, pts_in, i0);
-            affine_t p1 = has_pair ? pair_load<CURVE, FIRST>(entries, pts_in, i0 + 1) : p0;
-            fe_t den;
-            pair_classify<CURVE>(p0, p1, has_pair, den);
-            pref[s - s0] = run;
+            store_fe(pref + (size_t)s * 32, run);
+            kinds[s] = kind;
             run = F::mul(run, den);
         }
     }
-    // ---- one inversion for the CTA: scans of the per-thread totals, total inverted by thread 0
     sh_pre[threadIdx.x] = run;
     sh_suf[threadIdx.x] = run;
     __syncthreads();
@@ -628,57 +634,127 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_add(const uint32_t *__res
         if (dn) sh_suf[threadIdx.x] = b;
         __syncthreads();
     }
-    if (threadIdx.x == 0) sh_inv = F::inv_gcd(sh_pre[PAIR_THREADS - 1]);
+    // 1 / (own total) = 1 / (CTA total) * (product of the other threads' totals)
+    fe_t f = F::one();
+    if (threadIdx.x > 0) f = sh_pre[threadIdx.x - 1];
+    if (threadIdx.x + 1 < PAIR_THREADS) f = F::mul(f, sh_suf[threadIdx.x + 1]);
+    store_fe(thread_factor + (size_t)t * 32, f);
+    if (threadIdx.x == 0) store_fe(cta_total + (size_t)blockIdx.x * 32, sh_pre[PAIR_THREADS - 1]);
+}
+
+// middle pass, one CTA: cta_factor[c] = 1 / (total of CTA c) = 1 / (grid total) * (product of all other CTA totals);
+// ONE inversion for the whole round
+template <int CURVE>
+__global__ void __launch_bounds__(PAIR_MID_THREADS) k_pair_mid(const uint32_t *__restrict__ off_out, uint32_t nkeys,
+                                                               const uint8_t *__restrict__ cta_total, uint8_t *__restrict__ cta_factor) {
+    using F = typename Curve<CURVE>::F;
+    __shared__ fe_t sh[PAIR_MID_THREADS];
+    __shared__ fe_t carry_s;
+    const uint32_t M_out = off_out[nkeys];
+    const uint32_t ncta = (uint32_t)(((uint64_t)M_out + PAIR_THREADS * PAIR_B - 1) / ((uint64_t)PAIR_THREADS * PAIR_B));
+    if (ncta == 0) return;
+    const uint32_t nchunks = (ncta + PAIR_MID_THREADS - 1) / PAIR_MID_THREADS;
+    // forward: cta_factor[c] = product of totals before c
+    if (threadIdx.x == 0) carry_s = F::one();
     __syncthreads();
-    // inverse of this thread's own total: inv(total) * (product of the others) = inv(T) * pre[t-1] * suf[t+1]
-    fe_t rinv = sh_inv;
-    if (threadIdx.x > 0) rinv = F::mul(rinv, sh_pre[threadIdx.x - 1]);
-    if (threadIdx.x + 1 < PAIR_THREADS) rinv = F::mul(rinv, sh_suf[threadIdx.x + 1]);
-    // ---- phase B: back-substitution, slopes, sums
-    if (s0 < s1) {
-        // walk the slots backwards; the bucket of s1 - 1 by binary search again
-        uint32_t lo = 0, hi = nkeys - 1;
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (off_out[mid + 1] > s1 - 1) hi = mid; else lo = mid + 1;
+    for (uint32_t ch = 0; ch < nchunks; ch++) {
+        const uint32_t c = ch * PAIR_MID_THREADS + threadIdx.x;
+        fe_t v = c < ncta ? load_fe(cta_total + (size_t)c * 32) : F::one();
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < PAIR_MID_THREADS; d <<= 1) {
+            fe_t a;
+            const bool up = (int)threadIdx.x >= d;
+            if (up) a = F::mul(sh[threadIdx.x], sh[threadIdx.x - d]);
+            __syncthreads();
+            if (up) sh[threadIdx.x] = a;
+            __syncthreads();
         }
-        uint32_t k = lo, bstart = off_out[k];
+        const fe_t carry = carry_s;
+        fe_t excl = threadIdx.x > 0 ? F::mul(carry, sh[threadIdx.x - 1]) : carry;
+        if (c < ncta) store_fe(cta_factor + (size_t)c * 32, excl);
+        __syncthreads();
+        if (threadIdx.x == PAIR_MID_THREADS - 1) carry_s = F::mul(carry, sh[threadIdx.x]);
+        __syncthreads();
+    }
+    // grid total and its inverse
+    __shared__ fe_t inv_s;
+    if (threadIdx.x == 0) inv_s = F::inv_gcd(carry_s);
+    __syncthreads();
+    // backward: multiply in the product of totals after c, then the inverse
+    if (threadIdx.x == 0) carry_s = inv_s;          // carry = inv * (product of totals after the current chunk)
+    __syncthreads();
+    for (uint32_t chi = nchunks; chi-- > 0;) {
+        const uint32_t c = chi * PAIR_MID_THREADS + threadIdx.x;
+        fe_t v = c < ncta ? load_fe(cta_total + (size_t)c * 32) : F::one();
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < PAIR_MID_THREADS; d <<= 1) {       // inclusive suffix products
+            fe_t a;
+            const bool dn = (int)threadIdx.x + d < PAIR_MID_THREADS;
+            if (dn) a = F::mul(sh[threadIdx.x], sh[threadIdx.x + d]);
+            __syncthreads();
+            if (dn) sh[threadIdx.x] = a;
+            __syncthreads();
+        }
+        const fe_t carry = carry_s;
+        fe_t after = threadIdx.x + 1 < PAIR_MID_THREADS ? F::mul(carry, sh[threadIdx.x + 1]) : carry;
+        if (c < ncta) store_fe(cta_factor + (size_t)c * 32, F::mul(load_fe(cta_factor + (size_t)c * 32), after));
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = F::mul(carry, sh[0]);
+        __syncthreads();
+    }
+}
+
+// backward pass: back-substitution of the shared inverse, slopes, sums
+template <int CURVE, bool FIRST>
+__global__ void __launch_bounds__(PAIR_THREADS) k_pair_bwd(const uint32_t *__restrict__ off_in, const uint32_t *__restrict__ off_out,
+                                                           uint32_t nkeys, const uint32_t *__restrict__ entries,
+                                                           const affine_t *__restrict__ pts_in, const uint8_t *__restrict__ pref,
+                                                           const uint8_t *__restrict__ kinds, const uint8_t *__restrict__ thread_factor,
+                                                           const uint8_t *__restrict__ cta_factor, affine_t *__restrict__ pts_out) {
+    using F = typename Curve<CURVE>::F;
+    const uint32_t M_out = off_out[nkeys];
+    const uint32_t t = blockIdx.x * PAIR_THREADS + threadIdx.x;
+    const uint64_t s64 = (uint64_t)t * PAIR_B;
+    if (s64 >= M_out) return;
+    const uint32_t s0 = (uint32_t)s64;
+    const uint32_t s1 = (s64 + PAIR_B < M_out) ? (uint32_t)(s64 + PAIR_B) : M_out;
+    fe_t rinv = F::mul(load_fe(cta_factor + (size_t)blockIdx.x * 32), load_fe(thread_factor + (size_t)t * 32));
+    // bucket of the last slot, then walk backwards
+    uint32_t k, bstart;
+    {
+        PairWalk w; w.init(off_out, nkeys, s1 - 1);
+        k = w.k; bstart = off_out[k];
+    }
 #pragma unroll 1
-        for (uint32_t s = s1; s-- > s0;) {
-            if (s < bstart) {
-                k--; bstart = off_out[k];
-                if (s < bstart) {                  // empty buckets behind: binary search for the bucket holding slot s
-                    uint32_t blo = 0, bhi = k;
-                    while (blo < bhi) {
-                        uint32_t mid = (blo + bhi) >> 1;
-                        if (off_out[mid + 1] > s) bhi = mid; else blo = mid + 1;
-                    }
-                    k = blo; bstart = off_out[k];
-                }
-            }
-            const uint32_t j = s - bstart;
-            const uint32_t i0 = off_in[k] + 2 * j;
-            const bool has_pair = i0 + 1 < off_in[k + 1];
-            affine_t p0 = pair_load<CURVE, FIRST>(entries, pts_in, i0);
-            affine_t p1 = has_pair ? pair_load<CURVE, FIRST>(entries, pts_in, i0 + 1) : p0;
-            fe_t den;
-            const int kind = pair_classify<CURVE>(p0, p1, has_pair, den);
-            const fe_t dinv = F::mul(rinv, pref[s - s0]);     // 1 / den of this slot
-            rinv = F::mul(rinv, den);
-            affine_t r;
-            if (kind == 0) r = p0;
-            else if (kind == 1) r = p1;
-            else if (kind == 4) { r.x = F::zero(); r.y = F::zero(); }
-            else {
-                fe_t num;
-                if (kind == 2) num = F::sub(p1.y, p0.y);
-                else { fe_t xx = F::sqr(p0.x); num = F::add(F::dbl(xx), xx); }
-                const fe_t lam = F::mul(num, dinv);
-                r.x = F::sub(F::sub(F::sqr(lam), p0.x), p1.x);
-                r.y = F::sub(F::mul(lam, F::sub(p0.x, r.x)), p0.y);
-            }
-            store_fe(&pts_out[s].x, r.x); store_fe(&pts_out[s].y, r.y);
+    for (uint32_t s = s1; s-- > s0;) {
+        if (s < bstart) {
+            k--; bstart = off_out[k];
+            if (s < bstart) { PairWalk w; w.init(off_out, nkeys, s); k = w.k; bstart = off_out[k]; }
         }
+        const uint32_t i0 = off_in[k] + 2 * (s - bstart);
+        const uint8_t kind = kinds[s];
+        affine_t r;
+        if (kind == PAIR_PASS0 || kind == PAIR_PASS1) {
+            const uint32_t i = kind == PAIR_PASS0 ? i0 : i0 + 1;
+            r.x = pair_load_x<FIRST>(entries, pts_in, i);
+            r.y = pair_load_y<CURVE, FIRST>(entries, pts_in, i);
+        } else if (kind == PAIR_IDENT) {
+            r = affine_identity_marker();
+        } else {
+            const fe_t x0 = pair_load_x<FIRST>(entries, pts_in, i0), y0 = pair_load_y<CURVE, FIRST>(entries, pts_in, i0);
+            const fe_t x1 = pair_load_x<FIRST>(entries, pts_in, i0 + 1);
+            fe_t den, num;
+            if (kind == PAIR_ADD) { den = F::sub(x1, x0); num = F::sub(pair_load_y<CURVE, FIRST>(entries, pts_in, i0 + 1), y0); }
+            else { den = F::dbl(y0); fe_t xx = F::sqr(x0); num = F::add(F::dbl(xx), xx); }
+            const fe_t dinv = F::mul(rinv, load_fe(pref + (size_t)s * 32));
+            rinv = F::mul(rinv, den);
+            const fe_t lam = F::mul(num, dinv);
+            r.x = F::sub(F::sub(F::sqr(lam), x0), x1);
+            r.y = F::sub(F::mul(lam, F::sub(x0, r.x)), y0);
+        }
+        store_fe(&pts_out[s].x, r.x); store_fe(&pts_out[s].y, r.y);
     }
 }
 
