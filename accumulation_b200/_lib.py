@@ -10,7 +10,7 @@ SO_PATH = os.environ.get("ACCMSM_SO") or os.path.join(HERE, "libaccmsm.so")   # 
 
 # every symbol include/accmsm.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "accmsm_init", "accmsm_destroy", "accmsm_host_alloc", "accmsm_host_free", "accmsm_strerror", "accmsm_last_error", "accmsm_set_window_bits",
+    "accmsm_init", "accmsm_destroy", "accmsm_host_alloc", "accmsm_host_free", "accmsm_strerror", "accmsm_last_error", "accmsm_set_window_bits", "accmsm_set_ipa_fold",
     "accmsm_kernel_launches", "accmsm_last_timings", "accmsm_stage_name",
     "accmsm_register_bases", "accmsm_release_bases", "accmsm_register_synthetic_bases", "accmsm_download_bases", "accmsm_precompute_bases",
     "accmsm_msm", "accmsm_msm_oneshot", "accmsm_msm_batch", "accmsm_commit", "accmsm_msm_dev", "accmsm_msm_partial_dev", "accmsm_combine_partials_dev",

@@ -80,6 +80,9 @@ struct accmsm_ctx {
     DevBuf<uint32_t> pair_off[2];
     DevBuf<uint8_t> pair_pref, pair_kinds, pair_tfac, pair_ctot, pair_cfac;
     int affine_rounds_override = -1;            // development knob (ACCMSM_AFFINE_ROUNDS), -1 = automatic
+    DevBuf<xyzz_t> fold_partial;                // IpaPC::open folded-key materialisation (ipa.cuh)
+    DevBuf<uint32_t> fold_flag;
+    int ipa_fold_rounds = 5, ipa_fold_min_log = 14;   // accmsm_set_ipa_fold
     affine_t *d_out_affine = nullptr;
     uint32_t *d_out_inf = nullptr;
     uint64_t *h_out = nullptr;   // pinned: 8 u64 affine + 1 u64 inf + 16 u64 partial
@@ -142,6 +145,49 @@ uint32_t pick_window_bits(const accmsm_ctx *ctx, size_t n) {
 // The window table is used whenever the key has one (unless an explicit window override asks for something else),
 // also for MSMs much shorter than the key: a short MSM is bound by the latency of its tail, and the table path has no
 // Horner over windows (~256 dependent doublings, ~0.9 ms), only a reduction over mostly empty buckets.
+// Builds (or rebuilds) the window table of a key: table[w * n + i] = 2^(c w) * base_i.  Caller holds ctx->mu.
+// `storage` (optional): a caller-owned buffer of *storage_cap records that is grown when too small and then holds the
+// table -- the IPA open sessions recycle theirs, because cudaMalloc / cudaFree in the middle of an opening stall.
+int precompute_table(accmsm_ctx *ctx, Bases &B, int window_bits, affine_t **storage = nullptr, size_t *storage_cap = nullptr) {
+    if (!storage) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (B.d_table) { cudaFree(B.d_table); B.d_table = nullptr; B.pre_c = B.pre_nwin = 0; }
+    }
+    if (B.n == 0) return ACCMSM_OK;
+    // auto: measured best per key size (profiles/r01l_window_rule.txt).  Scalars are < 2^254, so what counts is
+    // ceil(254 / c) non-empty windows and the bucket count 2^(c-1) of the single bucket set: c = 17 has 15 working
+    // windows (the 16th covers bit 255 only) over 2^16 buckets and wins from 2^15 to 2^19 points; c = 20 (13 windows,
+    // 2^19 buckets) from 2^20 on, where the insertions dominate the reduction.
+    uint32_t lg = 0;
+    while ((size_t(1) << (lg + 1)) <= B.n) lg++;
+    uint32_t c = window_bits ? (uint32_t)window_bits : lg >= 20 ? 20u : lg >= 15 ? 17u : lg >= 13 ? 15u : 10u;
+    uint32_t nwin = (256 + c - 1) / c;
+    if ((size_t)nwin * B.n >= (size_t(1) << 31)) return fail_arg(ctx, "precompute_bases: windows * n must be < 2^31");
+    affine_t *table = nullptr;
+    const size_t records = (size_t)nwin * B.n;
+    if (storage) {
+        if (*storage_cap < records) {
+            if (*storage) cudaFree(*storage);
+            *storage = nullptr; *storage_cap = 0;
+            CU(ctx, cudaMalloc(storage, records * sizeof(affine_t)));
+            *storage_cap = records;
+        }
+        table = *storage;
+    } else {
+        CU(ctx, cudaMalloc(&table, records * sizeof(affine_t)));
+    }
+    uint32_t blocks = (uint32_t)((B.n + 127) / 128);
+    if (B.curve == 0) k_precompute<0><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+    else k_precompute<1><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+    ctx->launches++;
+    if (!storage) {      // sessions stay asynchronous: the table is consumed on the same stream
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(table); CU(ctx, e); }
+    }
+    B.d_table = table; B.pre_c = c; B.pre_nwin = nwin;
+    return ACCMSM_OK;
+}
+
 bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
     (void)n;
     if (!B.d_table) return false;
@@ -587,6 +633,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release();
     for (int i = 0; i < 2; i++) { ctx->pair_pts[i].release(); ctx->pair_off[i].release(); }
+    ctx->fold_partial.release(); ctx->fold_flag.release();
     ctx->pair_pref.release(); ctx->pair_kinds.release(); ctx->pair_tfac.release(); ctx->pair_ctot.release(); ctx->pair_cfac.release();
     for (int i = 0; i < 2; i++) { ctx->red_sum[i].release(); ctx->red_wsum[i].release(); }
     if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
@@ -612,6 +659,14 @@ void accmsm_host_free(void *p) { if (p) cudaFreeHost(p); }
 int accmsm_set_window_bits(accmsm_ctx *ctx, int c) {
     if (!ctx || c < 0 || c > 16 || c == 1) return fail_arg(ctx, "window bits must be 0 (auto) or 2..16");
     ctx->window_bits = c;
+    return ACCMSM_OK;
+}
+
+int accmsm_set_ipa_fold(accmsm_ctx *ctx, int rounds, int min_log_n) {
+    if (!ctx || rounds < 0 || rounds > 10 || min_log_n < 0 || min_log_n > 31)
+        return fail_arg(ctx, "set_ipa_fold: rounds must be 0 (never) or 1..10, min_log_n 0..31");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->ipa_fold_rounds = rounds; ctx->ipa_fold_min_log = min_log_n;
     return ACCMSM_OK;
 }
 
@@ -677,30 +732,8 @@ int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     auto it = ctx->bases.find(handle);
     if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }
-    Bases &B = it->second;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (B.d_table) { cudaFree(B.d_table); B.d_table = nullptr; B.pre_c = B.pre_nwin = 0; }
-    if (B.n == 0) return ACCMSM_OK;
-    // auto: measured best per key size (profiles/r01l_window_rule.txt).  Scalars are < 2^254, so what counts is
-    // ceil(254 / c) non-empty windows and the bucket count 2^(c-1) of the single bucket set: c = 17 has 15 working
-    // windows (the 16th covers bit 255 only) over 2^16 buckets and wins from 2^15 to 2^19 points; c = 20 (13 windows,
-    // 2^19 buckets) from 2^20 on, where the insertions dominate the reduction.
-    uint32_t lg = 0;
-    while ((size_t(1) << (lg + 1)) <= B.n) lg++;
-    uint32_t c = window_bits ? (uint32_t)window_bits : lg >= 20 ? 20u : lg >= 15 ? 17u : lg >= 13 ? 15u : 10u;
-    uint32_t nwin = (256 + c - 1) / c;
-    if ((size_t)nwin * B.n >= (size_t(1) << 31)) return fail_arg(ctx, "precompute_bases: windows * n must be < 2^31");
-    affine_t *table = nullptr;
-    CU(ctx, cudaMalloc(&table, (size_t)nwin * B.n * sizeof(affine_t)));
-    uint32_t blocks = (uint32_t)((B.n + 127) / 128);
-    if (B.curve == 0) k_precompute<0><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
-    else k_precompute<1><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
-    ctx->launches++;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { cudaFree(table); CU(ctx, e); }
-    B.d_table = table; B.pre_c = c; B.pre_nwin = nwin;
-    return ACCMSM_OK;
+    return precompute_table(ctx, it->second, window_bits);
 }
 
 int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out) {

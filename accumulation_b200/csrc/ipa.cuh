@@ -105,4 +105,145 @@ __global__ void __launch_bounds__(256) k_ipa_fold_scalars(uint8_t *__restrict__ 
     store_fe(z0, F::add(load_fe(z0), F::mul(x, load_fe(z + (size_t)(i + h) * 32))));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Folded-key materialisation.  The unfolded rounds above cost one MSM over ALL n0 / 2 pairs per job in every round,
+// although the folded key of round j has only n0 / 2^j points.  After J rounds the folded key
+//     FK[p] = sum_{u < 2^J} C(u) * G[u * m + p],   p < m = n / 2^J,   C(u) = prod_{r <= J : bit (J - r) of u} xi_r
+// is materialised once and the session continues on it as on a freshly registered key (window table included).
+// All m outputs share the 2^J scalars C(u), so nothing is sorted per point: the scalars are cut into signed
+// sub-digits of `cs` bits INSIDE each window of the current key's table (table[w] = 2^(c w) G supplies the window
+// weight; G = ceil(c / cs) Horner groups supply the sub-digit weight), one tiny counting sort orders the
+// (u, w) pairs of every group by digit magnitude (k_fold_digits, one CTA), and k_fold_accumulate gives one thread
+// per (output, group, window slice) the classical running-sum walk  sum_d d * B_d  over that shared list: every lane
+// of a warp follows the same list, the loads table[w][u * m + p] are coalesced across p and there is no divergence.
+// k_fold_combine adds the slices, runs the Horner recombination over the groups and normalises.
+// Cost: n * nwin * G mixed additions (52 per key point for c = 20, J = 5) against J more unfolded rounds saved per
+// J rounds that follow.
+// ------------------------------------------------------------------------------------------------
+struct FoldShape {
+    uint32_t J;         // rounds folded at once; 2^J blocks of the current key are combined
+    uint32_t m;         // points of the folded key
+    uint32_t stride;    // points per window of the current key's table
+    uint32_t c, nwin;   // radix and windows of that table
+    uint32_t cs, G;     // sub-digit bits and sub-digits per table window
+    uint32_t WS;        // window slices: slice ws takes the windows w with w % WS == ws
+    uint32_t nbk;       // 2^(cs - 1): largest digit magnitude
+};
+constexpr uint32_t FOLD_MAX_KEYS = 8192;      // G * WS * (nbk + 1) list heads, held in shared memory by k_fold_digits
+constexpr int FOLD_THREADS = 128;
+ACC_D uint32_t fold_list(const FoldShape &f, uint32_t g, uint32_t ws, uint32_t d) { return (g * f.WS + ws) * (f.nbk + 1) + d; }
+ACC_D uint32_t fold_width(const FoldShape &f, uint32_t g) { return f.c - g * f.cs < f.cs ? f.c - g * f.cs : f.cs; }
+
+// One CTA.  entries[offsets[list] .. offsets[list + 1]) = (sign << 31 | w << 16 | u) of the pairs whose sub-digit g of
+// window w has magnitude d, list = fold_list(g, w % WS, d).  digits = scratch of 2^J * nwin * G words.
+template <int SFIELD>
+__global__ void __launch_bounds__(256) k_fold_digits(const uint8_t *__restrict__ challenges, FoldShape f,
+                                                      uint32_t *__restrict__ digits, uint32_t *__restrict__ offsets,
+                                                      uint32_t *__restrict__ entries) {
+    using F = Fp<SFIELD>;
+    __shared__ uint32_t heads[FOLD_MAX_KEYS + 1];
+    __shared__ uint32_t chunk_sum[256];
+    const uint32_t T = 1u << f.J, nlists = f.G * f.WS * (f.nbk + 1), tid = threadIdx.x;
+    for (uint32_t k = tid; k <= nlists; k += 256) heads[k] = 0;
+    __syncthreads();
+    for (uint32_t u = tid; u < T; u += 256) {
+        fe_t acc = F::one();
+        for (uint32_t r = 1; r <= f.J; r++)
+            if ((u >> (f.J - r)) & 1u) acc = F::mul(acc, load_fe(challenges + (size_t)(r - 1) * 32));
+        const fe_t s = F::from_mont(acc);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < f.nwin; w++) {
+            for (uint32_t g = 0; g < f.G; g++) {
+                const uint32_t width = fold_width(f, g), half = 1u << (width - 1);
+                const uint32_t raw = extract_bits(s.l, w * f.c + g * f.cs, width) + carry;
+                uint32_t enc;
+                if (raw > half) { uint32_t mag = (1u << width) - raw; carry = 1; enc = mag ? (mag | 0x80000000u) : 0u; }
+                else { carry = 0; enc = raw; }
+                digits[(size_t)(w * f.G + g) * T + u] = enc;
+                if (enc & 0x7fffffffu) atomicAdd(&heads[fold_list(f, g, w % f.WS, enc & 0x7fffffffu)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the list lengths: contiguous chunk per thread, 256-wide scan of the chunk sums
+    const uint32_t per = (nlists + 1 + 255) / 256, k0 = tid * per, k1 = k0 + per < nlists + 1 ? k0 + per : nlists + 1;
+    uint32_t sum = 0;
+    for (uint32_t k = k0; k < k1; k++) sum += heads[k];
+    chunk_sum[tid] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 256; d <<= 1) {
+        uint32_t v = tid >= d ? chunk_sum[tid - d] : 0u;
+        __syncthreads();
+        chunk_sum[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = chunk_sum[tid] - sum;
+    for (uint32_t k = k0; k < k1; k++) { uint32_t h = heads[k]; heads[k] = run; offsets[k] = run; run += h; }
+    __syncthreads();
+    for (uint32_t idx = tid; idx < T * f.nwin * f.G; idx += 256) {
+        const uint32_t u = idx % T, wg = idx / T, w = wg / f.G, g = wg % f.G;
+        const uint32_t enc = digits[idx], mag = enc & 0x7fffffffu;
+        if (!mag) continue;
+        const uint32_t pos = atomicAdd(&heads[fold_list(f, g, w % f.WS, mag)], 1u);
+        entries[pos] = (enc & 0x80000000u) | (w << 16) | u;
+    }
+}
+
+// grid (ceil(m / FOLD_THREADS), G * WS): partial[(g * WS + ws) * m + p] = sum_d d * B_d over the list of (g, ws),
+// B_d = sum of +-table[w][base + u * m + p] over the list entries of magnitude d
+template <int CURVE>
+__global__ void __launch_bounds__(FOLD_THREADS) k_fold_accumulate(const affine_t *__restrict__ table, FoldShape f,
+                                                                   const uint32_t *__restrict__ offsets,
+                                                                   const uint32_t *__restrict__ entries,
+                                                                   xyzz_t *__restrict__ partial) {
+    using Cv = Curve<CURVE>;
+    const uint32_t p = blockIdx.x * FOLD_THREADS + threadIdx.x;
+    if (p >= f.m) return;
+    const uint32_t gw = blockIdx.y, g = gw / f.WS;
+    const uint32_t *off = offsets + (size_t)gw * (f.nbk + 1);
+    xyzz_t running = Cv::identity(), total = Cv::identity();
+#pragma unroll 1
+    for (uint32_t d = 1u << (fold_width(f, g) - 1); d >= 1; d--) {
+        const uint32_t e1 = __ldg(off + d + 1);
+#pragma unroll 1
+        for (uint32_t e = __ldg(off + d); e < e1; e++) {
+            const uint32_t ent = __ldg(entries + e);
+            const uint32_t w = (ent >> 16) & 0x7fffu, u = ent & 0xffffu;
+            affine_t pt = load_affine(table + (size_t)w * f.stride + (size_t)u * f.m + p);
+            if (ent >> 31) pt.y = Cv::F::neg(pt.y);
+            Cv::madd(running, pt);
+        }
+        Cv::add(total, running);
+    }
+    store_xyzz(partial + (size_t)gw * f.m + p, total);
+}
+
+// one thread per output: FK[p] = sum_g 2^(cs g) sum_ws partial[g][ws][p], normalised; an identity result (possible
+// only for keys with a linear relation the challenges hit) is counted in *n_identity and the fold is abandoned
+template <int CURVE>
+__global__ void __launch_bounds__(FOLD_THREADS) k_fold_combine(const xyzz_t *__restrict__ partial, FoldShape f,
+                                                                affine_t *__restrict__ out, uint32_t *__restrict__ n_identity) {
+    using Cv = Curve<CURVE, FpCall>;
+    const uint32_t p = blockIdx.x * FOLD_THREADS + threadIdx.x;
+    if (p >= f.m) return;
+    xyzz_t acc = Cv::identity();
+#pragma unroll 1
+    for (int g = (int)f.G - 1; g >= 0; g--) {
+        if (!Cv::is_identity(acc)) {
+#pragma unroll 1
+            for (uint32_t b = 0; b < f.cs; b++) acc = Cv::dbl(acc);
+        }
+#pragma unroll 1
+        for (uint32_t ws = 0; ws < f.WS; ws++) {
+            xyzz_t t = load_xyzz(partial + (size_t)((uint32_t)g * f.WS + ws) * f.m + p);
+            Cv::add(acc, t);
+        }
+    }
+    affine_t a; uint32_t inf;
+    Cv::template to_affine<true>(acc, a, inf);
+    if (inf) atomicAdd(n_identity, 1u);
+    store_fe(&out[p].x, a.x); store_fe(&out[p].y, a.y);
+}
+
 }  // namespace accmsm

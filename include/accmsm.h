@@ -48,6 +48,12 @@ void *accmsm_host_alloc(size_t bytes);
 void  accmsm_host_free(void *p);
 /* tuning knobs (0 = automatic): window bits c for the next MSMs */
 int  accmsm_set_window_bits(accmsm_ctx *ctx, int c);
+/* IpaPC::open sessions: every `rounds` rounds the key folded by the challenges so far is materialised on the device
+ * (one shared-scalar batched MSM over the window table) and the session continues on it, while the key the rounds
+ * run on still has >= 2^min_log_n points.  rounds = 0: never (every round runs over the registered key).
+ * Defaults 5 and 14 (measured, profiles/r01p_ipa_open_fold.txt).  Results are identical either way.  Replaces the per-round key folding
+ * `key_l[i] + key_r[i].mul(xi)` of ark-poly-commit ipa_pc `open` (reached from src/ipa_pc_as/mod.rs:454-462). */
+int  accmsm_set_ipa_fold(accmsm_ctx *ctx, int rounds, int min_log_n);
 /* number of this library's kernels launched by ctx so far (bench.py reports it as gpu_launches) */
 uint64_t accmsm_kernel_launches(accmsm_ctx *ctx);
 /* CUDA-event time of the last call's device work, split by stage (ms); names in accmsm_stage_name */

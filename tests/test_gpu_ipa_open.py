@@ -124,3 +124,45 @@ def test_ipa_open_with_indexed_hiding_generator(ctx, curve, k):
     el, er, efk, ec, _ = oracle_open(curve, key, coeffs, z, hp, squeeze)
     assert all(same_point(x, y) for x, y in zip(b[0] + b[1], el + er)) and np.array_equal(b[2], efk) and np.array_equal(b[3], ec)
     ck.bases.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("k,rounds,min_log,indexed", [(6, 1, 2, False), (8, 2, 3, True), (10, 3, 4, False), (11, 5, 6, True),
+                                                      (11, 4, 11, True), (13, 5, 10, False), (12, 10, 12, True)])
+def test_ipa_open_with_materialised_folded_key(ctx, curve, k, rounds, min_log, indexed):
+    """accmsm_set_ipa_fold: every `rounds` rounds the session switches to the materialised folded key (one shared-scalar
+    batched MSM over the window table, k_fold_* in ipa.cuh).  (l, r) of every round, the final key and c stay bit-exact
+    with the oracle, which folds the key round by round like the reference (key_l[i] + xi key_r[i])."""
+    sf = cref.scalar_field(curve)
+    n = 1 << k
+    pts = cref.gen_points(curve, 80 + k, n + 1)
+    key, h = pts[:n], pts[n]
+    xi0 = cref.gen_scalars(sf, 81, 1, True).reshape(4)
+    hp, hp_inf = cref.point_mul(curve, h, 0, cref.from_mont(sf, xi0.reshape(1, 4)).reshape(4))
+    assert hp_inf == 0
+    coeffs = cref.gen_scalars(sf, 82 + k, n, True)
+    z = cref.gen_scalars(sf, 83, 1, True).reshape(4)
+    squeeze = sponge_stand_in(sf)
+    ck = ab.CommitterKey.new(ctx, curve, key, h, precompute=True)
+    launches0 = ctx.kernel_launches()
+    ctx.set_ipa_fold(0, 0)
+    plain = ab.InnerProductArgPC.open(ck, coeffs, z, None if indexed else hp, squeeze, log_d=k, xi0=xi0 if indexed else None)
+    launches_plain = ctx.kernel_launches() - launches0
+    ctx.set_ipa_fold(rounds, min_log)
+    try:
+        got = ab.InnerProductArgPC.open(ck, coeffs, z, None if indexed else hp, squeeze, log_d=k, xi0=xi0 if indexed else None)
+    finally:
+        ctx.set_ipa_fold()
+    assert ctx.kernel_launches() - launches0 - launches_plain != launches_plain      # the fold kernels did run
+    el, er, efk, ec, _ = oracle_open(curve, key, coeffs, z, hp, squeeze)
+    for res in (plain, got):
+        assert all(same_point(x, y) for x, y in zip(res[0] + res[1], el + er))
+        assert np.array_equal(res[2], efk) and np.array_equal(res[3], ec)
+    ck.bases.release()
+
+
+def test_set_ipa_fold_rejects_bad_arguments(ctx):
+    lib, h = ctx._lib, ctx._h
+    assert lib.accmsm_set_ipa_fold(h, -1, 17) == -2 and lib.accmsm_set_ipa_fold(h, 11, 17) == -2
+    assert lib.accmsm_set_ipa_fold(h, 5, 32) == -2 and lib.accmsm_set_ipa_fold(None, 5, 17) == -2
+    assert lib.accmsm_set_ipa_fold(h, 5, 17) == 0
