@@ -42,6 +42,12 @@ for curve in (0, 1):
     for _ in range(k):
         ctx.ipa_open_round(s); ctx.ipa_open_fold(s, xi, xi)
     ctx.ipa_open_finish(s)
+    ctx.set_ipa_fold(2, 2)          # materialise the folded key after rounds 2 and 4 (k_fold_* in ipa.cuh)
+    s = ctx.ipa_open_begin(key, scal(1 << k), k, scal(1)[0], hp)
+    for _ in range(k):
+        ctx.ipa_open_round(s); ctx.ipa_open_fold(s, xi, xi)
+    ctx.ipa_open_finish(s)
+    ctx.set_ipa_fold()
     key.release()
 ctx.close()
 print("sanitize_run done")
