@@ -235,6 +235,24 @@ class Context:
                                                     _p(_u64(point_mont)), _p(hp), C.byref(sess)), "ipa_open_begin")
         return int(sess.value)
 
+    def ipa_open_begin_shard(self, bases: "Bases", coeffs_mont, k: int, point_mont, h_prime_xy=None, shard_index: int = 0,
+                             log_shards: int = 0, z_scale_mont=None) -> int:
+        """session over ONE cyclic shard (indices = shard_index mod 2^log_shards) of a multi-GPU opening; k = log2 of
+        the shard length; z-vector = z_scale * point^(shard_index + 2^log_shards i)"""
+        cf = _u64(coeffs_mont).reshape(-1, 4)
+        sess = C.c_uint64(0)
+        hp = None if h_prime_xy is None else _u64(h_prime_xy)
+        zs = None if z_scale_mont is None else _u64(z_scale_mont)
+        self._check(self._lib.accmsm_ipa_open_begin_shard(self._h, C.c_uint64(bases.handle), _p(cf), C.c_size_t(cf.shape[0]), C.c_int(k),
+                                                          _p(_u64(point_mont)), _p(hp), C.c_uint32(shard_index), C.c_uint32(log_shards),
+                                                          _p(zs), C.byref(sess)), "ipa_open_begin_shard")
+        return int(sess.value)
+
+    def ipa_open_round_partial_dev(self, session: int, d_out_partials_ptr: int):
+        """this shard's un-normalised shares of (l, r): 2 x 16 u64 written to device memory (blocking)"""
+        self._check(self._lib.accmsm_ipa_open_round_partial_dev(self._h, C.c_uint64(session), C.c_void_p(d_out_partials_ptr)),
+                    "ipa_open_round_partial_dev")
+
     def ipa_open_use_hiding_generator(self, session: int, h_index: int, xi0_mont):
         self._check(self._lib.accmsm_ipa_open_use_hiding_generator(self._h, C.c_uint64(session), C.c_size_t(h_index), _p(_u64(xi0_mont))),
                     "ipa_open_use_hiding_generator")

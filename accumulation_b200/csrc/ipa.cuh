@@ -13,13 +13,21 @@
 
 namespace accmsm {
 
-// z_vec[i] = z^i by square-and-multiply on the index (one thread per element)
+// z_vec[i] = scale * z^(offset + (i << log_stride)) by square-and-multiply on the index (one thread per element).
+// offset < 2^log_stride; (0, 0, nullptr) gives the plain power vector.  The strided form is the z-vector of ONE cyclic
+// shard (index mod 2^log_stride == offset) of a multi-GPU opening; `scale` carries the factor the z-vector has picked
+// up in rounds that were folded elsewhere.
 template <int FIELD>
-__global__ void __launch_bounds__(256) k_powers(const uint8_t *__restrict__ z_ptr, uint32_t n, uint8_t *__restrict__ out) {
+__global__ void __launch_bounds__(256) k_powers(const uint8_t *__restrict__ z_ptr, uint32_t n, uint8_t *__restrict__ out,
+                                                 uint32_t log_stride, uint32_t offset, const uint8_t *__restrict__ scale) {
     using F = Fp<FIELD>;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fe_t zc = load_fe(z_ptr), pw = F::one();
+    fe_t zc = load_fe(z_ptr), pw = scale ? load_fe(scale) : F::one();
+    for (uint32_t b = 0; b < log_stride; b++) {
+        if ((offset >> b) & 1u) pw = F::mul(pw, zc);
+        zc = F::sqr(zc);
+    }
     for (uint32_t e = i; e; e >>= 1) {
         if (e & 1u) pw = F::mul(pw, zc);
         zc = F::sqr(zc);

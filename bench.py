@@ -312,6 +312,39 @@ def main():
         dist.all_reduce(tdec, op=dist.ReduceOp.MAX)
         decide[f"msm_sharded_strong_ms_2^{kk}"] = round(float(tdec[0]), 4)
         dkey.release()
+        # ipa-pc-as prove hot path sharded: IpaPC::open at degree 2^20 with key / coefficients / z-vector sharded
+        # cyclically (ShardedIpaOpen): per round one all-gather of 2 x 128-byte shares, last log2(N) rounds replicated
+        if not args.no_open and world & (world - 1) == 0:
+            import hashlib
+            from accumulation_b200.mirror import _int_to_fe
+            from accumulation_b200.sharded import ShardedIpaOpen
+
+            def squeeze_s(prev, l, r):
+                h = hashlib.blake2s(b"" if prev is None else prev.tobytes())
+                h.update(l[0].tobytes()); h.update(r[0].tobytes())
+                return _int_to_fe(1, int.from_bytes(h.digest()[:16], "little") | 1)
+
+            n_loc = (1 << kk) // world
+            tmp = ctx.register_synthetic_bases(ab.PALLAS, SEED + 5, n_loc, first_index=rank * n_loc)
+            hgen = ctx.register_synthetic_bases(ab.PALLAS, SEED + 6, 1)            # the same hiding generator on every rank
+            okey = ctx.register_bases(ab.PALLAS, np.concatenate([ctx.download_bases(tmp), ctx.download_bases(hgen)]))
+            tmp.release(); hgen.release()
+            okey.precompute()
+            so = ShardedIpaOpen(ctx, ab.PALLAS, okey, kk, rank=rank, world=world, hiding_index=n_loc, device=str(dev))
+            cf = rand_scalars(n_loc, SEED + 200 + rank)
+            xi0 = rand_scalars(1, SEED + 97).reshape(4)
+            z = rand_scalars(1, SEED + 98).reshape(4)
+            ts = []
+            for _ in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                so.open(cf, z, squeeze_s, xi0_mont=xi0)
+                barrier()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            tdec = torch.tensor([min(ts[1:])], dtype=torch.float64, device=dev)
+            dist.all_reduce(tdec, op=dist.ReduceOp.MAX)
+            decide[f"ipa_open_sharded_ms_2^{kk}"] = round(float(tdec[0]), 3)
+            okey.release()
 
     # ---- ipa-pc-as prove hot path: IpaPC::open on device (metric string: prove ms at degree 2^18), one GPU
     if rank == 0 and world == 1 and not args.no_open:

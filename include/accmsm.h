@@ -107,7 +107,11 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
 
 /* Scalars already resident in HBM (produced on the device by the vector kernels, or staged by the caller):
  * d_scalars is a DEVICE pointer on ctx's GPU; the work is enqueued on `stream` (a cudaStream_t, NULL = the
- * ctx stream) and the call blocks until the affine result is on the host. */
+ * ctx stream) and the call blocks until the affine result is on the host.
+ * NOTE for every `stream` argument of this header: the ctx stream is a non-blocking stream and is NOT ordered after
+ * work on the CUDA default stream.  A caller whose producer (e.g. an NCCL all-gather issued by torch) runs on the
+ * default stream passes that stream explicitly as cudaStreamLegacy ((cudaStream_t)0x1) or cudaStreamPerThread
+ * ((cudaStream_t)0x2), never NULL. */
 int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
                    int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf, void *stream);
 
@@ -150,9 +154,10 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
  *     finish() -> (final_comm_key, c)
  * round:  l = cm_commit(key_l, coeffs_r) + <coeffs_r, z_l> h'      r = cm_commit(key_r, coeffs_l) + <coeffs_l, z_r> h'
  * fold :  coeffs_l += xi^-1 coeffs_r;  z_l += xi z_r;  key_l += xi key_r (batch-normalised)
- * fold only enqueues; finish releases the session (also on error).  The key is never folded on the device: every
- * round's (l, r) and the final key are MSMs over the registered key (window table if built) with scalars
- * coefficient x product-of-challenges generated in registers, so results equal the folded-key computation exactly. */
+ * fold only enqueues; finish releases the session (also on error).  The key is never folded generator by generator:
+ * a round's (l, r) and the final key are MSMs over the registered key (window table if built) with scalars
+ * coefficient x product-of-challenges generated in registers, and every few rounds the folded key is materialised in
+ * one batched MSM (accmsm_set_ipa_fold) -- results equal the folded-key computation exactly. */
 int accmsm_ipa_open_begin(accmsm_ctx *ctx, uint64_t handle, const uint64_t *coeffs_mont, size_t n_coeffs, int k,
                           const uint64_t point_mont[4], const uint64_t h_prime_xy[8], uint64_t *session);
 /* Same session, but the polynomial being opened is built on the device: AtomicASForInnerProductArgPC::prove opens
@@ -171,6 +176,20 @@ int accmsm_ipa_open_round(accmsm_ctx *ctx, uint64_t session, uint64_t l_xy[8], u
                           uint64_t r_xy[8], uint8_t *r_inf);
 int accmsm_ipa_open_fold(accmsm_ctx *ctx, uint64_t session, const uint64_t xi_mont[4], const uint64_t xi_inv_mont[4]);
 int accmsm_ipa_open_finish(accmsm_ctx *ctx, uint64_t session, uint64_t final_key_xy[8], uint64_t c_mont[4]);
+
+/* Multi-GPU opening ("IPA open folding"): the key, the coefficients and the z-vector are sharded
+ * CYCLICALLY, shard g of G = 2^log_shards owns the indices i with i mod G == g, so the fold partners i and i + n/2 stay
+ * on one GPU until n/2 < G.  Each GPU runs an ordinary session of length 2^k / G over its shard:
+ *   begin_shard: z-vector of the shard, z_scale * point^(shard_index + G i); z_scale (nullable = 1) carries the factor
+ *                prod_r (1 + xi_r point^(n/2^r)) of rounds folded elsewhere, for the final log2(G) rounds that run
+ *                replicated on the G gathered (final key, coefficient) pairs;
+ *   round_partial_dev: this shard's un-normalised shares of (l, r) -> 2 x 16 u64 in DEVICE memory (blocking), to be
+ *                all-gathered (NCCL) and summed with accmsm_combine_partials_dev; fold / finish as usual.
+ * accumulation_b200/sharded.py::ShardedIpaOpen is the host side. */
+int accmsm_ipa_open_begin_shard(accmsm_ctx *ctx, uint64_t handle, const uint64_t *coeffs_mont, size_t n_coeffs, int k,
+                                const uint64_t point_mont[4], const uint64_t h_prime_xy[8], uint32_t shard_index,
+                                uint32_t log_shards, const uint64_t z_scale_mont[4], uint64_t *session);
+int accmsm_ipa_open_round_partial_dev(accmsm_ctx *ctx, uint64_t session, void *d_out_partials);
 
 /* ---- field-vector kernels (K3 materialised, K4, K5); all pointers HOST, Montgomery images -------------- */
 /* SuccinctCheckPolynomial::compute_coeffs (src/ipa_pc_as/mod.rs:400): out = 2^k elements */

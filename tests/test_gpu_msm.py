@@ -267,7 +267,8 @@ def test_device_resident_scalars_and_sharded_flow(ctx, keys):
     sc = cref.gen_scalars(cref.FQ, 300, n, True)
     d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
     exp = cref.commit(0, pts[:n], sc)
-    st = torch.cuda.current_stream().cuda_stream
+    from accumulation_b200.sharded import _stream_handle
+    st = _stream_handle()      # torch's default stream by its explicit handle (0 would mean the ctx stream)
     assert same_point(ctx.msm_dev(B, d_sc.data_ptr(), n, stream=st), exp)
     assert same_point(ctx.msm_dev(B, d_sc.data_ptr(), n), exp)
     world = 3
