@@ -198,6 +198,15 @@ class Context:
                                                           _p(out), C.byref(inf), C.c_void_p(stream)), "combine_partials_dev")
         return out, int(inf.value)
 
+    def combine_partials_batch_dev(self, curve: int, d_partials_ptr: int, k: int, m: int, stream: int = 0):
+        """k x m gathered partials (rank-major) -> [(xy, inf)] * m"""
+        out = np.empty((m, 8), dtype=np.uint64)
+        inf = np.zeros(m, dtype=np.uint8)
+        self._check(self._lib.accmsm_combine_partials_batch_dev(self._h, C.c_int(curve), C.c_void_p(d_partials_ptr), C.c_size_t(k),
+                                                                C.c_size_t(m), _p(out), _p(inf), C.c_void_p(stream)),
+                    "combine_partials_batch_dev")
+        return [(out[j], int(inf[j])) for j in range(m)]
+
     # ---- IPA decider tail
     def ipa_final_key(self, bases: "Bases", challenges_mont):
         ch = _u64(challenges_mont).reshape(-1, 4)

@@ -920,6 +920,25 @@ int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partia
     return fetch_affine(ctx, out_xy, out_inf, st);
 }
 
+int accmsm_combine_partials_batch_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k, size_t m, uint64_t *out_xy,
+                                      uint8_t *out_inf, void *stream) {
+    if (!ctx || !out_xy || !out_inf || !d_partials || k == 0 || m == 0 || m > MAX_JOBS || (curve != 0 && curve != 1))
+        return fail_arg(ctx, "combine_partials_batch: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (curve == 0) k_combine_batch<0><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_affine, ctx->d_out_inf);
+    else k_combine_batch<1><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_affine, ctx->d_out_inf);
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, m * 64, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(ctx->h_out + 8 * MAX_JOBS, ctx->d_out_inf, m * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    memcpy(out_xy, ctx->h_out, m * 64);
+    const uint32_t *inf = (const uint32_t *)(ctx->h_out + 8 * MAX_JOBS);
+    for (size_t j = 0; j < m; j++) out_inf[j] = inf[j] != 0;
+    return ACCMSM_OK;
+}
+
 static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_mont, int k, size_t coeff_offset, size_t n,
                    xyzz_t *d_partial, bool normalise, cudaStream_t st) {
     CU(ctx, ctx->misc.ensure(64 * 32));

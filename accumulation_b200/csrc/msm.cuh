@@ -929,6 +929,22 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
     }
 }
 
+// out[j] = normalise(sum_r partials[r * m + j]), j < m: the G-way add after an all-gather of m shares per rank
+// (rank-major, as the gather leaves them).  One CTA per output, one thread (G <= 16 additions + one inversion).
+template <int CURVE>
+__global__ void k_combine_batch(const xyzz_t *__restrict__ partials, uint32_t k, uint32_t m,
+                                affine_t *__restrict__ out_affine, uint32_t *__restrict__ out_inf) {
+    using Cv = Curve<CURVE>;
+    if (threadIdx.x != 0) return;
+    const uint32_t j = blockIdx.x;
+    xyzz_t acc = Cv::identity();
+    for (uint32_t r = 0; r < k; r++) { xyzz_t s = load_xyzz(partials + (size_t)r * m + j); Cv::add(acc, s); }
+    affine_t a; uint32_t inf;
+    Cv::template to_affine<true>(acc, a, inf);
+    store_fe(&out_affine[j].x, a.x); store_fe(&out_affine[j].y, a.y);
+    out_inf[j] = inf;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_precompute: table[w * n + i] = 2^(c w) * P_i in affine form, w < nwin.  One thread per base walks the
 // doubling chain in XYZZ, keeps the nwin - 1 intermediate points in local memory and normalises them with

@@ -184,13 +184,8 @@ class ShardedIpaOpen:
 
     def combine(self, all_partials):
         """all_partials: (world, 32) gathered shares -> ((l_xy, l_inf), (r_xy, r_inf)); every rank gets the same"""
-        import torch
-        ap = all_partials.reshape(self.world, 2, PARTIAL_WORDS)
-        st = _stream_handle()
-        out = []
-        for j in range(2):
-            part = ap[:, j, :].contiguous()
-            out.append(self.ctx.combine_partials_dev(self.curve, part.data_ptr(), self.world, stream=st))
+        ap = all_partials.contiguous()
+        out = self.ctx.combine_partials_batch_dev(self.curve, ap.data_ptr(), self.world, 2, stream=_stream_handle())
         return out[0], out[1]
 
     def fold(self, xi_mont, xi_inv_mont):

@@ -126,6 +126,10 @@ int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size
  * Enqueued on `stream` (NULL = the ctx stream); blocks until the affine result is on the host. */
 int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k,
                                 uint64_t out_xy[8], uint8_t *out_inf, void *stream);
+/* m results at once: d_partials holds k x m partials, rank-major (exactly what an all-gather of m shares per rank
+ * leaves); out_xy m x 8 u64, out_inf m bytes; m <= 8.  Used per round by the multi-GPU IpaPC::open for (l, r). */
+int accmsm_combine_partials_batch_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k, size_t m,
+                                      uint64_t *out_xy, uint8_t *out_inf, void *stream);
 
 /* ---- IPA decider tail (K3 fused into K2) --------------------------------------------------------------
  * IpaPC::check_individual_opening_challenges after succinct_check (reached from
