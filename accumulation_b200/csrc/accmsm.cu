@@ -195,7 +195,7 @@ bool use_table(const accmsm_ctx *ctx, const Bases &B, size_t n) {
 }
 
 constexpr uint32_t ACC_WARP_MAX_KEYS = 8192;        // warp-per-bucket accumulation up to this many buckets ...
-constexpr size_t ACC_WARP_MAX_ENTRIES = 1u << 16;   // ... and bucket insertions (measured crossover with the balanced kernel: 2^12 points)
+constexpr size_t ACC_WARP_MAX_ENTRIES = 1u << 17;   // ... and bucket insertions (measured: 0.106 vs 0.221 ms at 2^12 points, c = 10; one CTA per bucket loses beyond 8192 buckets)
 
 #ifndef RED_L0_BLK
 #define RED_L0_BLK 32     // threads per row / column sum of the first reduction level (one warp: 16-32 serial adds + 5 shuffle steps; measured best of 32/64/128/256)
@@ -296,9 +296,8 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
     }
     mark(ctx, ST_ACCUMULATE, st);
     if (sh.nkeys <= ACC_WARP_MAX_KEYS && n_entries <= ACC_WARP_MAX_ENTRIES) {
-        // short MSM: one warp per bucket, no slice merging (k_accumulate_warp in msm.cuh)
-        uint32_t blocks = (sh.nkeys * 32 + 255) / 256;
-        k_accumulate_warp<CURVE><<<blocks, 256, 0, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p, points, ctx->buckets.p);
+        // short MSM: one group of four replica warps per bucket, no slice merging (k_accumulate_warp_coop in msm.cuh)
+        k_accumulate_warp_coop<CURVE><<<sh.nkeys, 128, 0, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p, points, ctx->buckets.p);
         ctx->launches++;
         mark(ctx, ST_FIXUP, st);
     } else {
@@ -370,30 +369,38 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
             t0.ntasks = 2;
             t0.t[0] = SumTask{0, 0, R0, C0, C0, 1};          // R_hi = sum_lo B[hi][lo]
             t0.t[1] = SumTask{0, R0, C0, R0, 1, C0};         // C_lo = sum_hi B[hi][lo]
-            k_sums<CURVE, RED_L0_BLK><<<dim3(R0 + C0, nsets), RED_L0_BLK, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, scratch, R0 + C0, t0);
+            // first level: cooperative groups while the grid is small enough to be latency-bound (measured: 0.132 vs 0.147 ms
+            // with 256 outputs, 0.202 vs 0.175 ms with 512), plain warps when it is throughput-bound (2^19 buckets)
+            if ((R0 + C0) * nsets <= 320u)
+                k_sums_coop<CURVE><<<dim3(R0 + C0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, scratch, R0 + C0, t0);
+            else
+                k_sums<CURVE, RED_L0_BLK><<<dim3(R0 + C0, nsets), RED_L0_BLK, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, scratch, R0 + C0, t0);
             t1.ntasks = 4;
             t1.t[0] = SumTask{0, 0, R0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, R0 / 32, 1, 32};
             t1.t[2] = SumTask{R0, 64, C0 / 32, 32, 32, 1};   t1.t[3] = SumTask{R0, 96, 32, C0 / 32, 1, 32};
-            k_sums<CURVE, 32><<<dim3(R0 / 32 + C0 / 32 + 64, nsets), 32, 0, st>>>(scratch, R0 + C0, nullptr, leaf, 128, t1);
+            k_sums_coop<CURVE><<<dim3(R0 / 32 + C0 / 32 + 64, nsets), 128, 0, st>>>(scratch, R0 + C0, nullptr, leaf, 128, t1);
             ctx->launches += 2;
             nlevels = 2;
         } else if (N0 > 32) {
             t1.ntasks = 2;
             t1.t[0] = SumTask{0, 0, N0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, N0 / 32, 1, 32};
-            k_sums<CURVE, 32><<<dim3(N0 / 32 + 32, nsets), 32, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
+            k_sums_coop<CURVE><<<dim3(N0 / 32 + 32, nsets), 128, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
             ctx->launches++;
             nlevels = 1;
         } else {
             t1.ntasks = 1;
             t1.t[0] = SumTask{0, 0, N0, 1, 1, 1};
-            k_sums<CURVE, 32><<<dim3(N0, nsets), 32, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
+            k_sums_coop<CURVE><<<dim3(N0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
             ctx->launches++;
             nlevels = 0;
         }
         uint32_t s0 = 0;
         while (C0 && (1u << s0) < C0) s0++;
-        k_wsum_leaf<CURVE><<<nsets, 128, 0, st>>>(leaf, 128, nlevels, s0, sums);
-        ctx->launches++;
+        CU(ctx, ctx->red_sum[1].ensure((size_t)nsets * 5));
+        const uint32_t narr = nlevels == 2 ? 4 : nlevels == 1 ? 2 : 1;
+        k_leaf_scan_coop<CURVE><<<dim3(narr, nsets), 128, 0, st>>>(leaf, 128, ctx->red_sum[1].p);
+        k_leaf_combine_coop<CURVE><<<nsets, 256, 0, st>>>(ctx->red_sum[1].p, nlevels, s0, sums);
+        ctx->launches += 2;
         window_sums = sums;
     }
     mark(ctx, ST_FINISH, st);

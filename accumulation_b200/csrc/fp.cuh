@@ -367,7 +367,25 @@ template <int FIELD> struct Fp {
 // k_accumulate is 1.5x slower with calls).
 template <int FIELD> struct FpCall : Fp<FIELD> {
 #if defined(__CUDACC__)
-    static __device__ __noinline__ fe_t mul(const fe_t &a, const fe_t &b) { return Fp<FIELD>::mul(a, b); }
+    // operands and result travel in registers (scalars / a small struct by value), not through the local-memory stack
+    struct Regs8 { uint32_t r0, r1, r2, r3, r4, r5, r6, r7; };
+    static __device__ __noinline__ Regs8 mul_regs(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                                  uint32_t a6, uint32_t a7, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
+                                                  uint32_t b4, uint32_t b5, uint32_t b6, uint32_t b7) {
+        fe_t a, b;
+        a.l[0] = a0; a.l[1] = a1; a.l[2] = a2; a.l[3] = a3; a.l[4] = a4; a.l[5] = a5; a.l[6] = a6; a.l[7] = a7;
+        b.l[0] = b0; b.l[1] = b1; b.l[2] = b2; b.l[3] = b3; b.l[4] = b4; b.l[5] = b5; b.l[6] = b6; b.l[7] = b7;
+        fe_t r = Fp<FIELD>::mul(a, b);
+        Regs8 o{r.l[0], r.l[1], r.l[2], r.l[3], r.l[4], r.l[5], r.l[6], r.l[7]};
+        return o;
+    }
+    static __device__ __forceinline__ fe_t mul(const fe_t &a, const fe_t &b) {
+        Regs8 o = mul_regs(a.l[0], a.l[1], a.l[2], a.l[3], a.l[4], a.l[5], a.l[6], a.l[7],
+                           b.l[0], b.l[1], b.l[2], b.l[3], b.l[4], b.l[5], b.l[6], b.l[7]);
+        fe_t r;
+        r.l[0] = o.r0; r.l[1] = o.r1; r.l[2] = o.r2; r.l[3] = o.r3; r.l[4] = o.r4; r.l[5] = o.r5; r.l[6] = o.r6; r.l[7] = o.r7;
+        return r;
+    }
 #else
     static fe_t mul(const fe_t &a, const fe_t &b) { return Fp<FIELD>::mul(a, b); }
 #endif

@@ -18,9 +18,9 @@
 //                 boundaries are merged by a segmented scan in shared memory (hot buckets are
 //                 tree-reduced, never serialised: constant scalar vectors cost the same as random ones)
 //   k_fixup       merges the two boundary partials of every CTA
-//   k_accumulate_warp   short MSMs instead: one warp per bucket, no merging
+//   k_accumulate_warp_coop   short MSMs instead: four replica warps per bucket (coop.cuh), no merging
 //   k_sums /      bucket reduction sum_b b*B_b organised for depth: row / column sums of the bucket index (twice),
-//   k_wsum_leaf   then four 32-item weighted sums, one warp each
+//   k_leaf_*_coop then four 32-item weighted sums; latency-bound levels run as cooperative groups (coop.cuh)
 //   k_finish      (plain key: Horner combine of the window sums, c doublings per window), extra partials,
 //                 normalisation with a binary-GCD inversion
 #pragma once
@@ -331,6 +331,10 @@ ACC_D xyzz_t shfl_down_xyzz(const xyzz_t &p, int d) {
     return r;
 }
 
+}  // namespace accmsm
+#include "coop.cuh"   // needs load_fe / store_fe above
+namespace accmsm {
+
 // ------------------------------------------------------------------------------------------------
 // segmented inclusive scan of (id, point) slots in shared memory; slots with equal ids are contiguous.
 // After it, the last slot of every id-group holds the group's sum.  NS <= 2 * blockDim.x * SLOTS_PER_T.
@@ -485,37 +489,15 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
     }
 }
 
-// k_accumulate_warp: one warp per bucket, for short MSMs (few thousand buckets).  Lane j folds entries j, j + 32, ...
-// of its bucket, then the 32 partials are summed by a shuffle tree.  The balanced kernel above needs a segmented scan
-// (4-5 dependent point additions) plus k_fixup to merge slices; here a bucket costs ceil(m / 32) mixed adds and
-// log2(min(m, 32)) additions with no cross-warp merging at all -- about 2.5x fewer instructions per warp when the
-// whole problem is only a few warps per scheduler and therefore bound by latency, not throughput.
+// k_accumulate_warp_coop: one GROUP of four replica warps (coop.cuh, included further down) per bucket, for short MSMs
+// (a few thousand buckets).  Lane j folds entries j, j + 32, ... of its bucket, then the 32 partials are summed by a
+// shuffle tree; every addition is a cooperative one.  The balanced kernel above needs a segmented scan (4-5 dependent
+// point additions) plus k_fixup to merge slices; here nothing is merged across warps, which wins while the whole problem
+// is bound by latency, not throughput (0.106 vs 0.221 ms at 2^12 points).
 template <int CURVE>
-__global__ void __launch_bounds__(256) k_accumulate_warp(const uint32_t *__restrict__ offsets, uint32_t nkeys,
-                                                          const uint32_t *__restrict__ entries,
-                                                          const affine_t *__restrict__ bases, xyzz_t *__restrict__ buckets) {
-    using Cv = Curve<CURVE, FpCall>;
-    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (k >= nkeys) return;
-    const uint32_t b0 = offsets[k], b1 = offsets[k + 1];
-    if (b0 == b1) return;                      // empty bucket: never read by the reduction
-    xyzz_t acc = Cv::identity();
-    for (uint32_t p = b0 + lane; p < b1; p += 32) {
-        uint32_t ent = entries[p];
-        affine_t pt = load_affine(bases + (ent & 0x7fffffffu));
-        if (ent >> 31) pt.y = Cv::F::neg(pt.y);
-        Cv::madd(acc, pt);
-    }
-    const uint32_t m = b1 - b0;
-#pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
-        if ((uint32_t)d < m) {                 // warp-uniform: lanes >= m hold the identity
-            xyzz_t other = shfl_down_xyzz(acc, d);
-            if (lane < (uint32_t)d) Cv::add(acc, other);
-        }
-    }
-    if (lane == 0) store_xyzz(buckets + k, acc);
-}
+__global__ void __launch_bounds__(128) k_accumulate_warp_coop(const uint32_t *__restrict__ offsets, uint32_t nkeys,
+                                                               const uint32_t *__restrict__ entries,
+                                                               const affine_t *__restrict__ bases, xyzz_t *__restrict__ buckets);
 
 // ------------------------------------------------------------------------------------------------
 // Batch-affine pre-reduction.  One round halves the points of every bucket: neighbours
@@ -789,8 +771,8 @@ __global__ void __launch_bounds__(FIX_THREADS) k_fixup(const uint32_t *__restric
 //     W = C * sum_hi hi * R_hi + sum_lo lo * C_lo,      R_hi = sum_lo B[hi][lo],   C_lo = sum_hi B[hi][lo]
 // turns one weighted sum over R * C items into plain (tree) sums plus two weighted sums over R and C items.
 // Applied twice (nb <= 2^20 -> <= 1024 -> <= 32) the weighted sums left are over <= 32 items: one warp each.
-// k_sums does every plain-sum level (tasks describe rows / columns), k_wsum_leaf the four 32-item weighted sums and
-// the recombination.  Depth for 2^19 buckets: ~12 + 5 + 10 additions + 15 doublings, instead of ~90.
+// k_sums / k_sums_coop do every plain-sum level (tasks describe rows / columns), k_leaf_scan_coop the four 32-item
+// weighted sums and k_leaf_combine_coop the recombination.  Depth for 2^19 buckets: ~12 + 5 + 10 additions + 15 doublings, instead of ~90.
 // ------------------------------------------------------------------------------------------------
 
 struct SumTask {
@@ -851,54 +833,151 @@ __global__ void __launch_bounds__(BLK) k_sums(const xyzz_t *__restrict__ in, uin
     if (threadIdx.x == 0) store_xyzz(out + (size_t)set * out_set_stride + tk.out_off + o, acc);
 }
 
-// Leaf of the reduction, one CTA of 4 warps per bucket set.  leaf[set][a][j], a < 4, j < 32: warp a computes
-// W_a = sum_j j * leaf[a][j] (suffix scan, then a sum over the lanes >= 1) and T_a = sum_j leaf[a][j]; then
+// Leaf of the reduction per bucket set: leaf[set][a][j], a < 4, j < 32.  W_a = sum_j j * leaf[a][j] (suffix scan, then a
+// sum over the lanes >= 1), T_a = sum_j leaf[a][j], and
+//   nlevels == 2:  S = 2^s0 * (2^5 * W_0 + W_1) + (2^5 * W_2 + W_3) + T_0
+//   nlevels == 1:  S = 2^5 * W_0 + W_1 + T_0            nlevels == 0:  S = W_0 + T_0
+// (k_leaf_scan_coop / k_leaf_combine_coop below.)
+
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_accumulate_warp_coop(const uint32_t *__restrict__ offsets, uint32_t nkeys,
+                                                               const uint32_t *__restrict__ entries,
+                                                               const affine_t *__restrict__ bases, xyzz_t *__restrict__ buckets) {
+    using Cv = Curve<CURVE, FpCall>;
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch;
+    const uint32_t k = blockIdx.x, lane = threadIdx.x & 31;
+    CoopCtx c{&scratch, threadIdx.x >> 5, lane, 1, 0};
+    const uint32_t b0 = offsets[k], b1 = offsets[k + 1];
+    if (b0 == b1) return;                      // empty bucket (CTA-uniform): never read by the reduction
+    xyzz_t acc = Cv::identity();
+#pragma unroll 1
+    for (uint32_t p0 = b0; p0 < b1; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        xyzz_t q = Cv::identity();
+        if (p < b1) {
+            uint32_t ent = entries[p];
+            affine_t pt = load_affine(bases + (ent & 0x7fffffffu));
+            if (ent >> 31) pt.y = Cv::F::neg(pt.y);
+            q = Cv::from_affine(pt);
+        }
+        if (p0 == b0) acc = q; else Co::add(c, acc, q);
+    }
+    const uint32_t m = b1 - b0;
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        if ((uint32_t)d < m) {
+            xyzz_t other = shfl_down_xyzz(acc, d), t = acc;
+            if (lane >= (uint32_t)d) other = Cv::identity();
+            Co::add(c, t, other);
+            if (lane < (uint32_t)d) acc = t;
+        }
+    }
+    if (threadIdx.x == 0) store_xyzz(buckets + k, acc);
+}
+
+// Cooperative versions (coop.cuh: four replica warps per warp of points, ~3x lower latency per point operation).
+// k_sums_coop: one group (128 threads) per output.
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_sums_coop(const xyzz_t *__restrict__ in, uint32_t in_set_stride,
+                                                    const uint32_t *__restrict__ offsets, xyzz_t *__restrict__ out,
+                                                    uint32_t out_set_stride, SumTasks tasks) {
+    using Cv = Curve<CURVE, FpCall>;
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch;
+    uint32_t o = blockIdx.x, ti = 0;
+    while (ti + 1 < tasks.ntasks && o >= tasks.t[ti].n_out) { o -= tasks.t[ti].n_out; ti++; }
+    const SumTask tk = tasks.t[ti];
+    const uint32_t set = blockIdx.y, lane = threadIdx.x & 31;
+    CoopCtx c{&scratch, threadIdx.x >> 5, lane, 1, 0};
+    const xyzz_t *src = in + (size_t)set * in_set_stride;
+    const uint32_t *offs = offsets ? offsets + (size_t)set * in_set_stride : nullptr;
+    xyzz_t acc = Cv::identity();
+#pragma unroll 1
+    for (uint32_t j0 = 0; j0 < tk.len; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        xyzz_t b = Cv::identity();
+        if (j < tk.len) {
+            uint32_t idx = tk.in_off + o * tk.stride_out + j * tk.stride_len;
+            if (!offs || offs[idx + 1] != offs[idx]) b = load_xyzz(src + idx);
+        }
+        if (j0 == 0) acc = b; else Co::add(c, acc, b);
+    }
+    const uint32_t live = tk.len < 32 ? tk.len : 32;
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        if ((uint32_t)d < live) {
+            xyzz_t other = shfl_down_xyzz(acc, d), t = acc;
+            if (lane >= (uint32_t)d) other = Cv::identity();     // idle lanes must not wander into the P == Q path
+            Co::add(c, t, other);
+            if (lane < (uint32_t)d) acc = t;
+        }
+    }
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * out_set_stride + tk.out_off + o, acc);
+}
+
+// The leaf in cooperative form, two launches so that every group is its own CTA (a 16-warp CTA would be capped at 128
+// registers per thread and spill the points): k_leaf_scan_coop, grid (arrays, sets): W_a = sum_j j * leaf[a][j] and, for
+// a == 0, T_0 = sum_j leaf[0][j] -> ws[set][0..3], ws[set][4]; k_leaf_combine_coop, grid sets x 2 groups: the recombination
+// (formulas above).
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_leaf_scan_coop(const xyzz_t *__restrict__ leaf, uint32_t leaf_set_stride,
+                                                         xyzz_t *__restrict__ ws) {
+    using Cv = Curve<CURVE, FpCall>;
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch;
+    const uint32_t a = blockIdx.x, set = blockIdx.y, lane = threadIdx.x & 31;
+    CoopCtx c{&scratch, threadIdx.x >> 5, lane, 1, 0};
+    xyzz_t run = load_xyzz(leaf + (size_t)set * leaf_set_stride + a * 32 + lane);
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {            // suffix scan: run_j = sum_{i >= j} item_i
+        xyzz_t o = shfl_down_xyzz(run, d), t = run;
+        if (lane + d >= 32) o = Cv::identity();   // idle lanes must not wander into the P == Q path
+        Co::add(c, t, o);
+        if (lane + d < 32) run = t;
+    }
+    if (a == 0 && threadIdx.x == 0) store_xyzz(ws + (size_t)set * 5 + 4, run);
+    xyzz_t jr = lane >= 1 ? run : Cv::identity();   // sum_j j * item_j = sum_{j >= 1} run_j
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(jr, d), t = jr;
+        if (lane >= (uint32_t)d) o = Cv::identity();
+        Co::add(c, t, o);
+        if (lane < (uint32_t)d) jr = t;
+    }
+    if (threadIdx.x == 0) store_xyzz(ws + (size_t)set * 5 + a, jr);
+}
 //   nlevels == 2:  S = 2^s0 * (2^5 * W_0 + W_1) + (2^5 * W_2 + W_3) + T_0
 //   nlevels == 1:  S = 2^5 * W_0 + W_1 + T_0            nlevels == 0:  S = W_0 + T_0
 template <int CURVE>
-__global__ void __launch_bounds__(128) k_wsum_leaf(const xyzz_t *__restrict__ leaf, uint32_t leaf_set_stride, int nlevels,
-                                                    uint32_t s0, xyzz_t *__restrict__ out) {
-    using Cv = Curve<CURVE, FpCall>;
-    __shared__ xyzz_t W[4];
-    __shared__ xyzz_t T0;
-    const uint32_t set = blockIdx.x, a = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int narr = nlevels == 2 ? 4 : nlevels == 1 ? 2 : 1;
-    if ((int)a < narr) {
-        xyzz_t run = load_xyzz(leaf + (size_t)set * leaf_set_stride + a * 32 + lane);
+__global__ void __launch_bounds__(256) k_leaf_combine_coop(const xyzz_t *__restrict__ ws, int nlevels, uint32_t s0,
+                                                            xyzz_t *__restrict__ out) {
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch[2];
+    __shared__ xyzz_t H[2];
+    const uint32_t set = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = warp >> 2;
+    CoopCtx c{&scratch[g], warp & 3u, lane, 1 + g, 0};
+    const xyzz_t *w = ws + (size_t)set * 5;
+    if (nlevels >= 1 && (g == 0 || nlevels == 2)) {      // the two 2^5 recombinations, one group each
+        xyzz_t hi = load_xyzz(w + 2 * g);
 #pragma unroll 1
-        for (int d = 1; d < 32; d <<= 1) {            // suffix scan: run_j = sum_{i >= j} item_i
-            xyzz_t o = shfl_down_xyzz(run, d);
-            if (lane + d < 32) Cv::add(run, o);
-        }
-        if (a == 0 && lane == 0) T0 = run;
-        xyzz_t jr = lane >= 1 ? run : Cv::identity();   // sum_j j * item_j = sum_{j >= 1} run_j
-#pragma unroll 1
-        for (int d = 16; d >= 1; d >>= 1) {
-            xyzz_t o = shfl_down_xyzz(jr, d);
-            if (lane < (uint32_t)d) Cv::add(jr, o);
-        }
-        if (lane == 0) W[a] = jr;
+        for (int b = 0; b < 5; b++) hi = Co::dbl(c, hi);
+        xyzz_t lo = load_xyzz(w + 2 * g + 1);
+        Co::add(c, hi, lo);
+        if (c.role == 0 && lane == 0) H[g] = hi;
     }
     __syncthreads();
-    // the two 2^5 recombinations run in parallel (threads 0 and 32), the outer one on thread 0
-    if (nlevels >= 1 && lane == 0 && (a == 0 || (a == 1 && nlevels == 2))) {
-        xyzz_t hi = W[2 * a];
-        for (int b = 0; b < 5; b++) hi = Cv::dbl(hi);
-        xyzz_t lo = W[2 * a + 1];
-        Cv::add(hi, lo);
-        W[2 * a] = hi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        xyzz_t acc = W[0];
+    if (g == 0) {
+        xyzz_t acc = nlevels >= 1 ? H[0] : load_xyzz(w);
         if (nlevels == 2) {
-            for (uint32_t b = 0; b < s0; b++) acc = Cv::dbl(acc);
-            xyzz_t lo = W[2];
-            Cv::add(acc, lo);
+#pragma unroll 1
+            for (uint32_t b = 0; b < s0; b++) acc = Co::dbl(c, acc);
+            xyzz_t lo = H[1];
+            Co::add(c, acc, lo);
         }
-        xyzz_t t = T0;
-        Cv::add(acc, t);
-        store_xyzz(out + set, acc);
+        xyzz_t t = load_xyzz(w + 4);
+        Co::add(c, acc, t);
+        if (threadIdx.x == 0) store_xyzz(out + set, acc);
     }
 }
 
