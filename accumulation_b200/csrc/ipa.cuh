@@ -66,38 +66,51 @@ __global__ void __launch_bounds__(256) k_ipa_inner_final(const uint8_t *__restri
     }
 }
 
-// hp_table[j] = 2^(8 j) h' (XYZZ), j < 32: one thread, once per opening session
+// hp_table[j] = 2^(8 j) h' (XYZZ), j < 32, once per opening session: a chain of 248 dependent doublings, run by one
+// cooperative group (coop.cuh: 3 product phases per doubling instead of 9 serial products; 128 threads)
 template <int CURVE>
-__global__ void k_ipa_hp_table(const affine_t *__restrict__ hp, xyzz_t *__restrict__ table) {
-    using Cv = Curve<CURVE>;
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__global__ void __launch_bounds__(128) k_ipa_hp_table(const affine_t *__restrict__ hp, xyzz_t *__restrict__ table) {
+    using Cv = Curve<CURVE, FpCall>;
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch;
+    CoopCtx c{&scratch, threadIdx.x >> 5, threadIdx.x & 31u, 1, 0};
     xyzz_t cur = Cv::from_affine(load_affine(hp));
+#pragma unroll 1
     for (int j = 0; j < 32; j++) {
-        store_xyzz(table + j, cur);
-        if (j < 31) for (int b = 0; b < 8; b++) cur = Cv::dbl(cur);
+        if (threadIdx.x == 0) store_xyzz(table + j, cur);
+        if (j < 31) {
+#pragma unroll 1
+            for (int b = 0; b < 8; b++) cur = Co::dbl(c, cur);
+        }
     }
 }
-// out[y] = ip[y] * h' for y = 0, 1 (one warp each): lane j multiplies byte j of the scalar into 2^(8j) h',
-// then the 32 partial points are summed by a shuffle tree.
+// out[y] = ip[y] * h' for y = 0, 1 (one cooperative group each, 256 threads): lane j multiplies byte j of the scalar into
+// 2^(8j) h', then the 32 partial points are summed by a shuffle tree.
 template <int CURVE>
-__global__ void __launch_bounds__(64) k_ipa_hp_mul(const xyzz_t *__restrict__ table, const uint8_t *__restrict__ ip_canon,
-                                                    xyzz_t *__restrict__ out) {
-    using Cv = Curve<CURVE>;
-    const uint32_t y = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) k_ipa_hp_mul(const xyzz_t *__restrict__ table, const uint8_t *__restrict__ ip_canon,
+                                                     xyzz_t *__restrict__ out) {
+    using Cv = Curve<CURVE, FpCall>;
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch[2];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, y = warp >> 2;
+    CoopCtx c{&scratch[y], warp & 3u, lane, 1 + y, 0};
     const uint32_t byte = ip_canon[y * 32 + lane];
-    xyzz_t base = load_xyzz(table + lane);
+    const xyzz_t base = load_xyzz(table + lane);
     xyzz_t acc = Cv::identity();
 #pragma unroll 1
     for (int b = 7; b >= 0; b--) {
-        acc = Cv::dbl(acc);
-        if ((byte >> b) & 1u) Cv::add(acc, base);
+        acc = Co::dbl(c, acc);
+        xyzz_t q = ((byte >> b) & 1u) ? base : Cv::identity();
+        Co::add(c, acc, q);
     }
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, d);
-        if (lane < (uint32_t)d) Cv::add(acc, o);
+        xyzz_t o = shfl_down_xyzz(acc, d), t = acc;
+        if (lane >= (uint32_t)d) o = Cv::identity();
+        Co::add(c, t, o);
+        if (lane < (uint32_t)d) acc = t;
     }
-    if (lane == 0) store_xyzz(out + y, acc);
+    if ((warp & 3u) == 0 && lane == 0) store_xyzz(out + y, acc);
 }
 
 // coeffs[i] += xi_inv * coeffs[i + h] ;  z[i] += xi * z[i + h]
