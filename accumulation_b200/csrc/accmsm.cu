@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -90,7 +91,8 @@ struct accmsm_ctx {
     size_t stage_cap = 0;
     cudaEvent_t stage_done = nullptr;
     bool stage_busy = false;
-    std::vector<cudaEvent_t> chunk_events;   // download(): one per staged chunk
+    std::vector<cudaEvent_t> chunk_events;   // download() / chunked upload: one per 4 MiB chunk
+    cudaStream_t copy_stream = nullptr;      // chunked upload of large scalar vectors (msm_host_scalars)
     cudaEvent_t ev[ST_COUNT + 1];
     bool ev_valid[ST_COUNT + 1];
     float timings[ST_COUNT];
@@ -261,10 +263,19 @@ int launch_scan(accmsm_ctx *ctx, const uint32_t *counts, uint32_t nkeys, uint32_
 
 // The MSM pipeline after the digits kernel has been chosen.  Leaves the per-window sums combined into
 // either a device partial (d_partial) or the normalised affine result in ctx->d_out_affine/d_out_inf.
+// A host upload that is consumed chunk by chunk: feed(c) enqueues the copy of scalars [c * chunk_elems, ...) on the copy
+// stream and records events[c]; run_msm launches the digit kernel of chunk c behind that event, so the digit
+// decomposition of a chunk overlaps the PCIe transfer of the following ones.
+struct DigitChunks {
+    uint32_t nchunks = 0, chunk_elems = 0;
+    std::function<int(uint32_t)> feed;
+    const cudaEvent_t *events = nullptr;
+};
+
 template <int CURVE, class Src>
 int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const Src &src,
             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
-            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
+            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr, const DigitChunks *chunks = nullptr) {
     if (!d_out_aff) { d_out_aff = ctx->d_out_affine; d_out_inf = ctx->d_out_inf; }
     MsmShape sh = make_shape(ctx, B, jobs, n);
     const bool tabled = sh.ent_stride != 0;
@@ -281,9 +292,18 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
 
     mark(ctx, ST_DIGITS, st);
     CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), st));
-    {
+    if (chunks) {
+        for (uint32_t c = 0; c < chunks->nchunks; c++) {
+            const uint32_t i0 = c * chunks->chunk_elems, i1 = std::min<uint32_t>(sh.n, i0 + chunks->chunk_elems);
+            { int frc = chunks->feed(c); if (frc) return frc; }
+            CU(ctx, cudaStreamWaitEvent(st, chunks->events[c], 0));
+            dim3 blocks((i1 - i0 + 255) / 256, sh.njobs);
+            k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p, i0, i1);
+            ctx->launches++;
+        }
+    } else {
         dim3 blocks((sh.n + 255) / 256, sh.njobs);
-        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p);
+        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p, 0u, sh.n);
         ctx->launches++;
     }
     mark(ctx, ST_SCAN, st);
@@ -414,19 +434,20 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
 // run_msm over scalar vectors resident in HBM (one pointer per job), dispatched on the key's curve
 int msm_mem(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const uint8_t *const *d_scalars, int mont,
             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
-            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
+            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr, const DigitChunks *chunks = nullptr) {
     if (B.curve == 0) {
         MemScalars<1> src; src.montgomery = mont;
         for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
-        return run_msm<0>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+        return run_msm<0>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf, chunks);
     }
     MemScalars<0> src; src.montgomery = mont;
     for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
-    return run_msm<1>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+    return run_msm<1>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf, chunks);
 }
 int msm_mem1(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint8_t *d_scalars, int mont,
-             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st) {
-    return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st);
+             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
+             const DigitChunks *chunks = nullptr) {
+    return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr, chunks);
 }
 
 // Host -> device copy of a scalar / vector buffer.  Page-locked sources go straight to the DMA engine.  Pageable ones
@@ -551,7 +572,59 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
     clear_marks(ctx);
     CU(ctx, ctx->scalars.ensure(n * 32));
     mark(ctx, ST_H2D, st);
-    { int urc = upload(ctx, ctx->scalars.p, scalars, n * 32, st); if (urc) return urc; }
+    constexpr size_t CHUNK = 4u << 20;
+    const size_t bytes = n * 32;
+    if (bytes >= 4 * CHUNK) {
+        // large vectors: the upload runs on its own stream in 4 MiB chunks and the digit kernel follows it chunk by chunk,
+        // so only the first chunk's transfer is exposed (the 'digits' stage time then contains the rest of the transfer)
+        if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        DigitChunks ch;
+        ch.nchunks = (uint32_t)((bytes + CHUNK - 1) / CHUNK);
+        ch.chunk_elems = (uint32_t)(CHUNK / 32);
+        while (ctx->chunk_events.size() < ch.nchunks) {
+            cudaEvent_t ev;
+            CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->chunk_events.push_back(ev);
+        }
+        ch.events = ctx->chunk_events.data();
+        cudaPointerAttributes attr;
+        cudaError_t pe = cudaPointerGetAttributes(&attr, scalars);
+        bool pageable = pe != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        if (pe != cudaSuccess) (void)cudaGetLastError();
+        if (pageable) {
+            if (ctx->stage_busy) { CU(ctx, cudaEventSynchronize(ctx->stage_done)); ctx->stage_busy = false; }
+            if (ctx->stage_cap < bytes) {
+                if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+                ctx->h_stage = nullptr; ctx->stage_cap = 0;
+                CU(ctx, cudaMallocHost(&ctx->h_stage, bytes + bytes / 8));
+                ctx->stage_cap = bytes + bytes / 8;
+            }
+        }
+        const char *src = (const char *)scalars;
+        char *stage = (char *)ctx->h_stage;
+        uint8_t *dst = ctx->scalars.p;
+        cudaStream_t cs = ctx->copy_stream;
+        ch.feed = [=](uint32_t c) -> int {
+            const size_t off = (size_t)c * CHUNK, len = std::min(CHUNK, bytes - off);
+            const char *from = src + off;
+            if (pageable) {
+                const int parts = 4;
+#pragma omp parallel for num_threads(parts) schedule(static)
+                for (int p = 0; p < parts; p++) {
+                    size_t lo = len * p / parts, hi = len * (p + 1) / parts;
+                    memcpy(stage + off + lo, src + off + lo, hi - lo);
+                }
+                from = stage + off;
+            }
+            if (cudaMemcpyAsync(dst + off, from, len, cudaMemcpyHostToDevice, cs) != cudaSuccess) return ACCMSM_E_CUDA;
+            if (cudaEventRecord(ch.events[c], cs) != cudaSuccess) return ACCMSM_E_CUDA;
+            return ACCMSM_OK;
+        };
+        int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, nullptr, true, st, &ch);
+        if (rc) { ctx->last_error = "msm: chunked upload failed"; return rc; }
+        return fetch_affine(ctx, out_xy, out_inf, st);
+    }
+    { int urc = upload(ctx, ctx->scalars.p, scalars, bytes, st); if (urc) return urc; }
     int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, nullptr, true, st);
     if (rc) return rc;
     return fetch_affine(ctx, out_xy, out_inf, st);
@@ -649,6 +722,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);
     for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

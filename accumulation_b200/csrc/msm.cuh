@@ -177,10 +177,12 @@ ACC_D uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
 // ------------------------------------------------------------------------------------------------
 template <class Src>
 __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint8_t *__restrict__ base_is_identity,
-                                                 uint32_t *__restrict__ digits, uint32_t *__restrict__ hist) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                 uint32_t *__restrict__ digits, uint32_t *__restrict__ hist,
+                                                 uint32_t i0, uint32_t i1) {
+    // scalars [i0, i1) of every job: the whole vector in one launch, or one chunk of a host upload that is still in flight
+    uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t job = blockIdx.y;
-    if (i >= sh.n) return;
+    if (i >= i1) return;
     fe_t s = src.canonical(job, i);
     if (base_is_identity && base_is_identity[msm_base_index(sh, job, i)]) s = Fp<0>::zero();   // identity bases contribute nothing
     digits += (size_t)job * sh.nwin * sh.n;

@@ -200,7 +200,13 @@ def main():
     def step_dev():
         return sh.msm_dev(d_sc, montgomery=False)
 
+    h_np = h_sc.numpy().view(np.uint64)            # the same page-locked buffer as seen by the C-ABI
+
     def step_e2e():
+        # N = 1: the reference-facing C-ABI call accmsm_msm with a HOST pointer (upload in 4 MiB chunks on a copy stream, the
+        # digit kernel follows chunk by chunk, result read back); N > 1: pinned copy to the shard's GPU + partial + gather
+        if world == 1:
+            return ctx.msm(sh.bases, h_np, montgomery=False, n=count)
         return sh.msm_host(h_sc, d_stage, montgomery=False)
 
     # ---- warm-up (also sizes the workspace) and parity of the thing being timed

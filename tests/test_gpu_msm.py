@@ -460,3 +460,31 @@ def test_experimental_batch_affine_rounds(monkeypatch):
             B.release()
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_chunked_upload_overlapping_the_digit_kernel(ctx, pinned):
+    """Host scalar vectors of >= 16 MiB go up in 4 MiB chunks on a copy stream with the digit kernel following chunk by
+    chunk (msm_host_scalars); ragged last chunk, pageable (staged by several threads) and page-locked sources, result
+    bit-exact with the oracle and with the same MSM from device-resident scalars."""
+    import torch
+    n = (1 << 19) + 4097
+    key = ctx.register_synthetic_bases(0, 77, n)
+    key.precompute()
+    sc = cref.gen_scalars(cref.FQ, 78, n, True)
+    if pinned:
+        buf = ab.pinned_array((n, 4))
+        buf[:] = sc
+        src = buf
+    else:
+        src = sc
+    got = ctx.msm(key, src)
+    again = ctx.msm(key, src)                         # staging buffer and events are reused
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    dev = ctx.msm_dev(key, d_sc.data_ptr(), n)
+    assert same_point(got, dev) and same_point(again, dev)
+    pts = ctx.download_bases(key)
+    assert same_point(got, cref.commit(0, pts, sc))
+    if pinned:
+        ab.release_pinned(buf)
+    key.release()
