@@ -341,9 +341,9 @@ namespace accmsm {
 // segmented inclusive scan of (id, point) slots in shared memory; slots with equal ids are contiguous.
 // After it, the last slot of every id-group holds the group's sum.  NS <= 2 * blockDim.x * SLOTS_PER_T.
 // ------------------------------------------------------------------------------------------------
-template <int CURVE, int PER_T>
+template <int CURVE, int PER_T, template <int> class FT = Fp>
 ACC_D void seg_scan(xyzz_t *pt, const uint32_t *id, uint32_t ns) {
-    using Cv = Curve<CURVE>;
+    using Cv = Curve<CURVE, FT>;
     // Hillis-Steele in place.  A step reads slot i - d and writes slot i; the slots are swept in PER_T
     // phases from the top stripe down, so a phase only ever reads slots that this step has not written
     // yet (writes of a phase land in its own stripe, reads come from it or from lower stripes) and one
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(FIX_THREADS) k_fixup(const uint32_t *__restric
         slot_pt[i] = load_xyzz(cta_parts + i);
     }
     __syncthreads();
-    seg_scan<CURVE, FIX_PER_T>(slot_pt, slot_id, ns);
+    seg_scan<CURVE, FIX_PER_T, FpCall>(slot_pt, slot_id, ns);      // one pass over ~600 slots: latency-bound, keep the code small
     for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
         uint32_t id = slot_id[i];
         if (id == NONE_ID) continue;
