@@ -488,3 +488,24 @@ def test_chunked_upload_overlapping_the_digit_kernel(ctx, pinned):
     if pinned:
         ab.release_pinned(buf)
     key.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("precompute", [False, True])
+def test_reduction_tree_meets_equal_and_opposite_points(ctx, curve, precompute):
+    """Every base is the SAME point and every scalar a distinct small digit, so every bucket holds exactly that point (or
+    its negative): the bucket reduction then adds P + P and P + (-P) at every level of its shuffle trees -- the
+    exceptional branches of the (cooperative) addition that random inputs never reach."""
+    sf = cref.scalar_field(curve)
+    g = cref.gen_points(curve, 4242, 1)
+    for n, neg_every in ((512, 0), (512, 2), (300, 3), (31, 0), (2, 2)):
+        pts = np.repeat(g, n, axis=0)
+        vals = [i + 1 for i in range(n)]
+        q = pyref.Q_PALLAS_SCALAR if sf == cref.FQ else pyref.P_PALLAS_BASE
+        ints_ = [(q - v) if (neg_every and i % neg_every == 0) else v for i, v in enumerate(vals)]
+        sc = fe_mont(sf, ints_)
+        key = ctx.register_bases(curve, pts)
+        if precompute:
+            key.precompute()
+        assert same_point(ctx.msm(key, sc), cref.commit(curve, pts, sc))
+        key.release()
