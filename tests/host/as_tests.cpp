@@ -118,6 +118,13 @@ int main() {
             CHECK((tag + "ipa open: h' as a point == h' as (hiding index, xi_0)").c_str(),
                   p1.l_vec == p2.l_vec && p1.r_vec == p2.r_vec && p1.final_comm_key == p2.final_comm_key && p1.c == p2.c);
         }
+        {   // the materialised folded key (accmsm_set_ipa_fold) changes nothing in the proof: forced every 2 rounds here
+            ctx->check(accmsm_set_ipa_fold(ctx->raw(), 2, 2), "set_ipa_fold");
+            IpaProofCore pf = InnerProductArgPC::open(ipa_ck, coeffs, k, z, hgen, squeeze);
+            ctx->check(accmsm_set_ipa_fold(ctx->raw(), 5, 14), "set_ipa_fold");
+            CHECK((tag + "ipa open: same proof with the folded key materialised every 2 rounds").c_str(),
+                  pf.l_vec == proof.l_vec && pf.r_vec == proof.r_vec && pf.final_comm_key == proof.final_comm_key && pf.c == proof.c);
+        }
         SuccinctCheckPolynomial h{proof.round_challenges};
         CHECK((tag + "ipa check: final_comm_key == cm_commit(key, h.compute_coeffs())").c_str(), InnerProductArgPC::check_final_key(ipa_ck, h, proof.final_comm_key));
         Affine bad_key = proof.final_comm_key; bad_key.y[2] ^= 4;
