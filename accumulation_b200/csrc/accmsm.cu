@@ -96,6 +96,19 @@ struct accmsm_ctx {
     cudaEvent_t ev[ST_COUNT + 1];
     bool ev_valid[ST_COUNT + 1];
     float timings[ST_COUNT];
+    // One workspace per ctx, but `*_dev` entry points may only ENQUEUE on a caller stream: ws_done is recorded after
+    // every enqueue that touches the workspace and every later user on a different stream waits on it first.
+    cudaEvent_t ws_done = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_pending = false;
+    // small host arguments (challenges, xi, randomizers: <= 1 KiB) are copied into a ring of page-locked slots before
+    // the async H2D, so a caller that passes page-locked memory may reuse its buffer as soon as the call returns
+    static constexpr int ARG_SLOTS = 16;
+    static constexpr size_t ARG_SLOT_BYTES = 1024;
+    uint8_t *h_args = nullptr;
+    cudaEvent_t arg_done[ARG_SLOTS] = {nullptr};
+    bool arg_used[ARG_SLOTS] = {false};
+    int arg_next = 0;
 };
 
 namespace {
@@ -134,6 +147,32 @@ void collect_timings(accmsm_ctx *ctx) {
         }
         prev = i;
     }
+}
+
+// workspace ordering across streams (see accmsm_ctx::ws_done)
+int ws_acquire(accmsm_ctx *ctx, cudaStream_t st) {
+    if (ctx->ws_pending && ctx->ws_stream != st) CU(ctx, cudaStreamWaitEvent(st, ctx->ws_done, 0));
+    ctx->ws_stream = st;
+    return ACCMSM_OK;
+}
+int ws_release(accmsm_ctx *ctx, cudaStream_t st) {
+    CU(ctx, cudaEventRecord(ctx->ws_done, st));
+    ctx->ws_stream = st; ctx->ws_pending = true;
+    return ACCMSM_OK;
+}
+// async H2D of a small host argument through a ctx-owned page-locked slot (the caller's buffer is free on return)
+int upload_small(accmsm_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return ACCMSM_OK;
+    if (bytes > accmsm_ctx::ARG_SLOT_BYTES) { CU(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st)); CU(ctx, cudaStreamSynchronize(st)); return ACCMSM_OK; }
+    const int slot = ctx->arg_next;
+    ctx->arg_next = (slot + 1) % accmsm_ctx::ARG_SLOTS;
+    if (ctx->arg_used[slot]) CU(ctx, cudaEventSynchronize(ctx->arg_done[slot]));
+    uint8_t *h = ctx->h_args + (size_t)slot * accmsm_ctx::ARG_SLOT_BYTES;
+    memcpy(h, h_src, bytes);
+    CU(ctx, cudaMemcpyAsync(d_dst, h, bytes, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaEventRecord(ctx->arg_done[slot], st));
+    ctx->arg_used[slot] = true;
+    return ACCMSM_OK;
 }
 
 uint32_t pick_window_bits(const accmsm_ctx *ctx, size_t n) {
@@ -289,6 +328,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
     CU(ctx, ctx->offsets.ensure(sh.nkeys + 1));
     CU(ctx, ctx->cursor.ensure(sh.nkeys));
     CU(ctx, ctx->buckets.ensure(sh.nkeys));
+    { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
 
     mark(ctx, ST_DIGITS, st);
     CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), st));
@@ -428,7 +468,7 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
                                              d_partial, d_out_aff, d_out_inf);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
-    return ACCMSM_OK;
+    return ws_release(ctx, st);
 }
 
 // run_msm over scalar vectors resident in HBM (one pointer per job), dispatched on the key's curve
@@ -667,7 +707,9 @@ int accmsm_init(accmsm_ctx **out, int device) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
     for (int i = 0; i <= ST_COUNT; i++) { cudaEventCreate(&ctx->ev[i]); ctx->ev_valid[i] = false; }
     cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming);
-    bool ok = cudaMalloc(&ctx->d_out_affine, MAX_JOBS * sizeof(affine_t)) == cudaSuccess &&
+    cudaEventCreateWithFlags(&ctx->ws_done, cudaEventDisableTiming);
+    for (int i = 0; i < accmsm_ctx::ARG_SLOTS; i++) cudaEventCreateWithFlags(&ctx->arg_done[i], cudaEventDisableTiming);
+    bool ok = cudaMallocHost(&ctx->h_args, accmsm_ctx::ARG_SLOTS * accmsm_ctx::ARG_SLOT_BYTES) == cudaSuccess && cudaMalloc(&ctx->d_out_affine, MAX_JOBS * sizeof(affine_t)) == cudaSuccess &&
               cudaMalloc(&ctx->d_out_inf, MAX_JOBS * sizeof(uint32_t)) == cudaSuccess &&
               cudaMallocHost(&ctx->h_out, (MAX_JOBS * 9 + 32) * sizeof(uint64_t)) == cudaSuccess;
     // shared-memory opt-in and resident CTAs per SM for the accumulate kernels
@@ -721,6 +763,9 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);
+    if (ctx->ws_done) cudaEventDestroy(ctx->ws_done);
+    for (int i = 0; i < accmsm_ctx::ARG_SLOTS; i++) if (ctx->arg_done[i]) cudaEventDestroy(ctx->arg_done[i]);
+    if (ctx->h_args) cudaFreeHost(ctx->h_args);
     for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
@@ -937,7 +982,7 @@ int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *el
     CU(ctx, ctx->scalars.ensure((n + 1) * 32));
     mark(ctx, ST_H2D, st);
     if (n) { int urc = upload(ctx, ctx->scalars.p, elems_mont, n * 32, st); if (urc) return urc; }
-    CU(ctx, cudaMemcpyAsync(ctx->scalars.p + n * 32, randomizer_mont, 32, cudaMemcpyHostToDevice, st));
+    { int urc = upload_small(ctx, ctx->scalars.p + n * 32, randomizer_mont, 32, st); if (urc) return urc; }
     MsmJobs jobs(0);
     jobs.tail_base = (uint32_t)hiding_index;
     const uint8_t *ptr = ctx->scalars.p;
@@ -974,10 +1019,11 @@ int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size
     clear_marks(ctx);
     int rc;
     if (n == 0) {
+        { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
         if (B->curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, (xyzz_t *)d_out_partial, nullptr, nullptr);
         else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, (xyzz_t *)d_out_partial, nullptr, nullptr);
         ctx->launches++;
-        rc = ACCMSM_OK;
+        rc = ws_release(ctx, st);
     } else {
         rc = msm_mem1(ctx, *B, offset, n, (const uint8_t *)d_scalars, scalars_montgomery, nullptr, 0, (xyzz_t *)d_out_partial, false, st);
     }
@@ -994,6 +1040,7 @@ int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partia
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     // stage marks of a preceding accmsm_*_partial_dev on the same stream are kept (bench.py reads them)
+    { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
     mark(ctx, ST_FINISH, st);
     if (curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
     else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
@@ -1008,6 +1055,7 @@ int accmsm_combine_partials_batch_dev(accmsm_ctx *ctx, int curve, const void *d_
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
     if (curve == 0) k_combine_batch<0><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_affine, ctx->d_out_inf);
     else k_combine_batch<1><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_affine, ctx->d_out_inf);
     ctx->launches++;
@@ -1023,7 +1071,8 @@ int accmsm_combine_partials_batch_dev(accmsm_ctx *ctx, int curve, const void *d_
 static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_mont, int k, size_t coeff_offset, size_t n,
                    xyzz_t *d_partial, bool normalise, cudaStream_t st) {
     CU(ctx, ctx->misc.ensure(64 * 32));
-    if (k) CU(ctx, cudaMemcpyAsync(ctx->misc.p, challenges_mont, (size_t)k * 32, cudaMemcpyHostToDevice, st));
+    { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
+    if (k) { int urc = upload_small(ctx, ctx->misc.p, challenges_mont, (size_t)k * 32, st); if (urc) return urc; }
     if (B.curve == 0) { IpaScalars<1> src{ctx->misc.p, k, (uint32_t)coeff_offset}; return run_msm<0>(ctx, B, MsmJobs(0), n, src, nullptr, 0, d_partial, normalise, st); }
     IpaScalars<0> src{ctx->misc.p, k, (uint32_t)coeff_offset};
     return run_msm<1>(ctx, B, MsmJobs(0), n, src, nullptr, 0, d_partial, normalise, st);

@@ -44,7 +44,7 @@ template <int CURVE, template <int> class FT = Fp> struct Curve {
         fe_t xx = F::sqr(p.x);
         fe_t m = F::add(F::dbl(xx), xx);
         r.x = F::sub(F::sub(F::sqr(m), s), s);
-        r.y = F::sub(F::mul(m, F::sub(s, r.x)), F::mul(w, p.y));
+        r.y = F::mul2sub(m, F::sub(s, r.x), w, p.y);
         r.zz = v; r.zzz = w;
         return r;
     }
@@ -59,7 +59,7 @@ template <int CURVE, template <int> class FT = Fp> struct Curve {
         fe_t xx = F::sqr(p.x);
         fe_t m = F::add(F::dbl(xx), xx);
         r.x = F::sub(F::sub(F::sqr(m), s), s);
-        r.y = F::sub(F::mul(m, F::sub(s, r.x)), F::mul(w, p.y));
+        r.y = F::mul2sub(m, F::sub(s, r.x), w, p.y);
         r.zz = F::mul(v, p.zz);
         r.zzz = F::mul(w, p.zzz);
         return r;
@@ -81,7 +81,7 @@ template <int CURVE, template <int> class FT = Fp> struct Curve {
         fe_t ppp = F::mul(pp_, pp);
         fe_t q = F::mul(acc.x, pp);
         fe_t x3 = F::sub(F::sub(F::sub(F::sqr(r), ppp), q), q);
-        fe_t y3 = F::sub(F::mul(r, F::sub(q, x3)), F::mul(acc.y, ppp));
+        fe_t y3 = F::mul2sub(r, F::sub(q, x3), acc.y, ppp);
         acc.zz = F::mul(acc.zz, pp);
         acc.zzz = F::mul(acc.zzz, ppp);
         acc.x = x3; acc.y = y3;
@@ -105,7 +105,7 @@ template <int CURVE, template <int> class FT = Fp> struct Curve {
         fe_t ppp = F::mul(pp_, pp);
         fe_t qq = F::mul(u1, pp);
         fe_t x3 = F::sub(F::sub(F::sub(F::sqr(r), ppp), qq), qq);
-        fe_t y3 = F::sub(F::mul(r, F::sub(qq, x3)), F::mul(s1, ppp));
+        fe_t y3 = F::mul2sub(r, F::sub(qq, x3), s1, ppp);
         acc.zz = F::mul(F::mul(acc.zz, q.zz), pp);
         acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), ppp);
         acc.x = x3; acc.y = y3;

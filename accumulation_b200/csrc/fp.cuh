@@ -248,22 +248,26 @@ template <int FIELD> struct Fp {
                 ev[4] = nev[4];
             }
             // V += q * m, q = -V mod 2^32, m = [1, M1, M2, M3, 0, 0, 0, 2^30]
-            uint32_t q = 0u - lo32(ev[0]);
-            ev[0] = add_cc64(ev[0], (uint64_t)q);
-            ev[1] = addc_cc64(ev[1], mulw(q, P::M2));
-            ev[2] = addc_cc64(ev[2], ACC_MUL_WIDE_RIPPLES >= 2 ? mulw(q, k0) : 0ull);
-            ev[3] = addc_cc64(ev[3], ACC_MUL_WIDE_RIPPLES >= 3 ? mulw(q, k0) : 0ull);
-            ev[4] = addc64(ev[4], 0);
-            od[0] = add_cc64(od[0], mulw(q, P::M1));
-            od[1] = addc_cc64(od[1], mulw(q, P::M3));
-            od[2] = addc_cc64(od[2], ACC_MUL_WIDE_RIPPLES >= 1 ? mulw(q, k0) : 0ull);
-#if ACC_MUL_SHIFT_TOP
-            od[3] = addc64(od[3], pack64(q << 30, q >> 2));     // q * 2^30 on the ALU pipe instead of an IMAD.WIDE
-#else
-            od[3] = addc64(od[3], mulw(q, MOD_L7));
-#endif
+            reduce_round(ev, od, k0);
         }
-        fe_t r;  // (EV + OD 2^32) / 2^32, lo32(ev[0]) == 0
+        return assemble(ev, od);
+    }
+    // One Montgomery reduction round on the two accumulators: V += q * m with q = -V mod 2^32 (the low word becomes 0).
+    static ACC_HD void reduce_round(uint64_t (&ev)[5], uint64_t (&od)[4], uint32_t k0) {
+        uint32_t q = 0u - lo32(ev[0]);
+        ev[0] = add_cc64(ev[0], (uint64_t)q);
+        ev[1] = addc_cc64(ev[1], mulw(q, P::M2));
+        ev[2] = addc_cc64(ev[2], ACC_MUL_WIDE_RIPPLES >= 2 ? mulw(q, k0) : 0ull);
+        ev[3] = addc_cc64(ev[3], ACC_MUL_WIDE_RIPPLES >= 3 ? mulw(q, k0) : 0ull);
+        ev[4] = addc64(ev[4], 0);
+        od[0] = add_cc64(od[0], mulw(q, P::M1));
+        od[1] = addc_cc64(od[1], mulw(q, P::M3));
+        od[2] = addc_cc64(od[2], ACC_MUL_WIDE_RIPPLES >= 1 ? mulw(q, k0) : 0ull);
+        od[3] = addc64(od[3], mulw(q, MOD_L7));
+    }
+    // (EV + OD 2^32) / 2^32 with lo32(ev[0]) == 0, then one conditional subtraction (value < 2m)
+    static ACC_HD fe_t assemble(const uint64_t (&ev)[5], const uint64_t (&od)[4]) {
+        fe_t r;
         r.l[0] = add_cc(hi32(ev[0]), lo32(od[0]));
         r.l[1] = addc_cc(lo32(ev[1]), hi32(od[0]));
         r.l[2] = addc_cc(hi32(ev[1]), lo32(od[1]));
@@ -275,7 +279,105 @@ template <int FIELD> struct Fp {
         reduce_once(r);
         return r;
     }
-    static ACC_HD fe_t sqr(const fe_t &a) { return mul(a, a); }
+
+    // Squaring: a^2 = sum_i a_i 2^(32 i) * (a_i 2^(32 i) + 2 A_{>i}) with A_{>i} the limbs above i.  2 A_{>i} has the limbs
+    // [a_{i+1} << 1, d_{i+2}, .., d_7] where d = limbs of 2a (2a < 2^256), so row i of the interleaved product needs only
+    // the 8 - i limb products at positions >= i; the skipped ones leave plain carry ripples.  36 instead of 64 limb
+    // products, same reduction.  Bounds: the row operand is < 2a, so V < 2a + m < 2^256 after every round and the result
+    // is < a^2 / R + m < 2m.
+    static ACC_HD fe_t sqr(const fe_t &A) {
+        const uint32_t *a = A.l;
+        uint32_t d[8], s[8];      // d = 2a, s[j] = a[j] << 1 (d[j] with the bit shifted in from limb j - 1 cleared)
+        d[0] = s[0] = a[0] << 1;
+#pragma unroll
+        for (int j = 1; j < 8; j++) { s[j] = a[j] << 1; d[j] = s[j] | (a[j - 1] >> 31); }
+        uint64_t ev[5], od[4];
+        // row 0: a_0 * [a_0, s_1, d_2, .., d_7]
+        ev[0] = mulw(a[0], a[0]); od[0] = mulw(s[1], a[0]);
+        ev[1] = mulw(d[2], a[0]); od[1] = mulw(d[3], a[0]);
+        ev[2] = mulw(d[4], a[0]); od[2] = mulw(d[5], a[0]);
+        ev[3] = mulw(d[6], a[0]); od[3] = mulw(d[7], a[0]);
+        ev[4] = 0;
+        const uint32_t k0 = opaque_zero();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i > 0) {
+                // operand limb at position j of row i: 0 (j < i), a_i (j == i), s_{i+1} (j == i + 1), d_j (j > i + 1)
+                auto x = [&](int j) -> uint64_t {
+                    if (j < i) return 0ull;
+                    return mulw(j == i ? a[i] : j == i + 1 ? s[j] : d[j], a[i]);
+                };
+                uint64_t nev[5], nod[4];
+                uint32_t t_lo = add_cc(lo32(od[0]), hi32(ev[0]));
+                nod[0] = addc_cc64(ev[1], x(1));
+                nod[1] = addc_cc64(ev[2], x(3));
+                nod[2] = addc_cc64(ev[3], x(5));
+                nod[3] = addc64(ev[4], x(7));
+                nev[0] = add_cc64(pack64(t_lo, hi32(od[0])), x(0));
+                nev[1] = addc_cc64(od[1], x(2));
+                nev[2] = addc_cc64(od[2], x(4));
+                nev[3] = addc_cc64(od[3], x(6));
+                nev[4] = addc64(0, 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { ev[k] = nev[k]; od[k] = nod[k]; }
+                ev[4] = nev[4];
+            }
+            reduce_round(ev, od, k0);
+        }
+        return assemble(ev, od);
+    }
+
+    // (a b + c d) R^-1 with ONE reduction: both product rows are accumulated in every round.  V < a + c + m < 2^256
+    // after every round (inputs canonical), the result is < (a b + c d) / R + m < 2m.  96 + 64 limb products instead of
+    // 2 x 96, one conditional subtraction instead of two plus a field addition.
+    static ACC_HD fe_t mul2(const fe_t &A, const fe_t &B, const fe_t &C, const fe_t &D) {
+        const uint32_t *a = A.l, *b = B.l, *c = C.l, *dd = D.l;
+        uint64_t ev[5], od[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) { ev[s] = mulw(a[2 * s], b[0]); od[s] = mulw(a[2 * s + 1], b[0]); }
+        ev[0] = add_cc64(ev[0], mulw(c[0], dd[0]));
+        ev[1] = addc_cc64(ev[1], mulw(c[2], dd[0]));
+        ev[2] = addc_cc64(ev[2], mulw(c[4], dd[0]));
+        ev[3] = addc_cc64(ev[3], mulw(c[6], dd[0]));
+        ev[4] = addc64(0, 0);
+        od[0] = add_cc64(od[0], mulw(c[1], dd[0]));
+        od[1] = addc_cc64(od[1], mulw(c[3], dd[0]));
+        od[2] = addc_cc64(od[2], mulw(c[5], dd[0]));
+        od[3] = addc64(od[3], mulw(c[7], dd[0]));
+        const uint32_t k0 = opaque_zero();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i > 0) {
+                uint64_t nev[5], nod[4];
+                uint32_t t_lo = add_cc(lo32(od[0]), hi32(ev[0]));
+                nod[0] = addc_cc64(ev[1], mulw(a[1], b[i]));
+                nod[1] = addc_cc64(ev[2], mulw(a[3], b[i]));
+                nod[2] = addc_cc64(ev[3], mulw(a[5], b[i]));
+                nod[3] = addc64(ev[4], mulw(a[7], b[i]));
+                nev[0] = add_cc64(pack64(t_lo, hi32(od[0])), mulw(a[0], b[i]));
+                nev[1] = addc_cc64(od[1], mulw(a[2], b[i]));
+                nev[2] = addc_cc64(od[2], mulw(a[4], b[i]));
+                nev[3] = addc_cc64(od[3], mulw(a[6], b[i]));
+                nev[4] = addc64(0, 0);
+                nev[0] = add_cc64(nev[0], mulw(c[0], dd[i]));
+                nev[1] = addc_cc64(nev[1], mulw(c[2], dd[i]));
+                nev[2] = addc_cc64(nev[2], mulw(c[4], dd[i]));
+                nev[3] = addc_cc64(nev[3], mulw(c[6], dd[i]));
+                nev[4] = addc64(nev[4], 0);
+                nod[0] = add_cc64(nod[0], mulw(c[1], dd[i]));
+                nod[1] = addc_cc64(nod[1], mulw(c[3], dd[i]));
+                nod[2] = addc_cc64(nod[2], mulw(c[5], dd[i]));
+                nod[3] = addc64(nod[3], mulw(c[7], dd[i]));
+#pragma unroll
+                for (int k = 0; k < 4; k++) { ev[k] = nev[k]; od[k] = nod[k]; }
+                ev[4] = nev[4];
+            }
+            reduce_round(ev, od, k0);
+        }
+        return assemble(ev, od);
+    }
+    // a b - c d
+    static ACC_HD fe_t mul2sub(const fe_t &a, const fe_t &b, const fe_t &c, const fe_t &d) { return mul2(a, b, neg(c), d); }
 
     // into_repr(): Montgomery image -> canonical integer = a * 1 * R^-1
     static ACC_HD fe_t from_mont(const fe_t &a) {
@@ -390,6 +492,9 @@ template <int FIELD> struct FpCall : Fp<FIELD> {
     static fe_t mul(const fe_t &a, const fe_t &b) { return Fp<FIELD>::mul(a, b); }
 #endif
     static ACC_HD fe_t sqr(const fe_t &a) { return mul(a, a); }
+    // the latency-bound kernels keep ONE product body in the instruction cache: no dedicated squaring / dual product
+    static ACC_HD fe_t mul2(const fe_t &a, const fe_t &b, const fe_t &c, const fe_t &d) { return Fp<FIELD>::add(mul(a, b), mul(c, d)); }
+    static ACC_HD fe_t mul2sub(const fe_t &a, const fe_t &b, const fe_t &c, const fe_t &d) { return Fp<FIELD>::sub(mul(a, b), mul(c, d)); }
     static ACC_HD fe_t inv(const fe_t &a) {
         using P = FieldParams<FIELD>;
         fe_t acc = Fp<FIELD>::one();

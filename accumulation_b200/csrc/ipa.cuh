@@ -113,14 +113,16 @@ __global__ void __launch_bounds__(256) k_ipa_hp_mul(const xyzz_t *__restrict__ t
     if ((warp & 3u) == 0 && lane == 0) store_xyzz(out + y, acc);
 }
 
-// coeffs[i] += xi_inv * coeffs[i + h] ;  z[i] += xi * z[i + h]
+// coeffs[i] += xi_inv * coeffs[i + h] ;  z[i] += xi * z[i + h].  The challenge and its inverse travel as kernel
+// arguments (no H2D copy from caller memory that could still be in flight when the caller reuses its buffer); thread 0
+// also records xi as challenge `round` of the session.
 template <int FIELD>
 __global__ void __launch_bounds__(256) k_ipa_fold_scalars(uint8_t *__restrict__ coeffs, uint8_t *__restrict__ z, uint32_t h,
-                                                           const uint8_t *__restrict__ xi, const uint8_t *__restrict__ xi_inv) {
+                                                           fe_t x, fe_t xinv, uint8_t *__restrict__ challenge_slot) {
     using F = Fp<FIELD>;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && challenge_slot) store_fe(challenge_slot, x);
     if (i >= h) return;
-    fe_t x = load_fe(xi), xinv = load_fe(xi_inv);
     uint8_t *c0 = coeffs + (size_t)i * 32, *z0 = z + (size_t)i * 32;
     store_fe(c0, F::add(load_fe(c0), F::mul(xinv, load_fe(coeffs + (size_t)(i + h) * 32))));
     store_fe(z0, F::add(load_fe(z0), F::mul(x, load_fe(z + (size_t)(i + h) * 32))));

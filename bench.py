@@ -97,6 +97,28 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def oracle_threads(world):
+    """host threads each rank's oracle leg may use (torchrun exports OMP_NUM_THREADS=1; undo it for the checker)"""
+    return max(1, (os.cpu_count() or 1) // max(world, 1))
+
+
+def gather_cpu_points(cref, dist, torch, dev, world, part):
+    """all-gather one CPU-computed affine point (xy, inf) per rank and add them with the oracle -> (xy, inf) on every rank"""
+    row = np.concatenate([np.asarray(part[0], dtype=np.uint64).reshape(8), np.array([part[1]], dtype=np.uint64)])
+    t = torch.from_numpy(row.view(np.int64).copy()).to(dev).reshape(1, 9)
+    out = torch.empty((world, 9), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, t)
+    rows = out.cpu().numpy().view(np.uint64)
+    acc = (rows[0, :8].copy(), int(rows[0, 8]))
+    for r in range(1, world):
+        acc = cref.point_add(0, acc[0], acc[1], rows[r, :8].copy(), int(rows[r, 8]))
+    return acc
+
+
+def same_pt(a, b):
+    return a is not None and b is not None and int(a[1]) == int(b[1]) and np.array_equal(np.asarray(a[0], np.uint64), np.asarray(b[0], np.uint64))
+
+
 def run_reference(args, rank, world):
     """--impl reference: the ark-ec VariableBaseMSM restatement on host cores, same config / metric / unit."""
     if rank != 0:
@@ -256,6 +278,16 @@ def main():
     t_dev_ms, t_e2e_ms = float(tt[0]), float(tt[1])
     launches = int(lt[0])
 
+    checks = {}
+    # ---- parity of the timed multi-GPU step: every rank restates the MSM of its own shard on the CPU (oracle), the N affine
+    #      partials are added on the CPU and compared with the combined GPU point (device-resident and end-to-end paths)
+    if world > 1 and not args.no_verify:
+        from oracle import cref
+        cref.set_num_threads(oracle_threads(world))
+        exp_weak = gather_cpu_points(cref, dist, torch, dev, world, cref.msm_ark(0, ctx.download_bases(key, 0, count), sc_np))
+        if rank == 0:
+            checks["weak_msm_equals_oracle"] = same_pt(res, exp_weak) and same_pt(res_e2e, exp_weak)
+
     # ---- ipa-pc-as decide tail (metric string: decide ms at degree 2^18, target 2^20), one GPU.  Each degree gets the
     #      key a trimmed CommitterKey of that degree would register: 2^k generators + the hiding generator
     decide = {}
@@ -299,13 +331,30 @@ def main():
             fk = dsh.ipa_final_key(ch, kk)
             barrier()
             ts.append((time.perf_counter() - t0) * 1e3)
+        if not args.no_verify:
+            # parity of the sharded decide tail: every rank restates its own slice on the CPU (h(X) coefficients of its
+            # range x its key shard), the CPU partials are added, and rank 0 compares; a corrupted challenge must reject
+            from oracle import cref
+            cref.set_num_threads(oracle_threads(world))
+            dpts = ctx.download_bases(dkey, 0, s_cnt)
+            coeffs = cref.from_mont(cref.FQ, cref.compute_coeffs(cref.FQ, ch)[s_lo:s_lo + s_cnt])
+            exp_fk = gather_cpu_points(cref, dist, torch, dev, world, cref.msm_ark(0, dpts, coeffs))
+            ch_bad = ch.copy(); ch_bad[3, 0] ^= np.uint64(1)
+            fk_bad = dsh.ipa_final_key(ch_bad, kk)
+            if rank == 0:
+                checks["sharded_decide_accepts_oracle_key"] = same_pt(fk, exp_fk)
+                checks["sharded_decide_rejects_corrupted_challenge"] = not same_pt(fk_bad, exp_fk)
         tdec = torch.tensor([statistics.median(ts)], dtype=torch.float64, device=dev)
         dist.all_reduce(tdec, op=dist.ReduceOp.MAX)
         decide[f"ipa_decide_tail_sharded_ms_2^{kk}"] = round(float(tdec[0]), 4)
         # config 5 strong scaling: ONE 2^20-point MSM sharded over all ranks (scalars resident in HBM)
         d_sl = d_sc[:s_cnt]
         for _ in range(3):
-            dsh.msm_dev(d_sl, montgomery=False)
+            strong_res = dsh.msm_dev(d_sl, montgomery=False)
+        if not args.no_verify:
+            exp_strong = gather_cpu_points(cref, dist, torch, dev, world, cref.msm_ark(0, dpts, sc_np[:s_cnt]))
+            if rank == 0:
+                checks["sharded_strong_msm_equals_oracle"] = same_pt(strong_res, exp_strong)
         ts = []
         for _ in range(10):
             flush.zero_()
@@ -330,6 +379,9 @@ def main():
                 h.update(l[0].tobytes()); h.update(r[0].tobytes())
                 return _int_to_fe(1, int.from_bytes(h.digest()[:16], "little") | 1)
 
+            if not args.no_verify:
+                # parity of the sharded opening at a small degree: over NCCL against the oracle's round-by-round folding
+                checks["sharded_open_equals_oracle_2^10"] = sharded_open_check(ctx, ab, rank, world, str(dev), 10)
             n_loc = (1 << kk) // world
             tmp = ctx.register_synthetic_bases(ab.PALLAS, SEED + 5, n_loc, first_index=rank * n_loc)
             hgen = ctx.register_synthetic_bases(ab.PALLAS, SEED + 6, 1)            # the same hiding generator on every rank
@@ -437,6 +489,11 @@ def main():
                                        "fe_mul microbenchmark (tools/ubench.cu), power-capped"}
     if cpu:
         out["cpu_baseline"] = cpu
+    if world > 1 and not args.no_verify:
+        verified = bool(checks) and all(checks.values())
+        out["verified_checks"] = checks
+        if not verified:
+            raise SystemExit(f"bench: a multi-GPU result differs from the oracle -- refusing to report a number: {checks}")
     if verified is not None:
         out["verified_vs_oracle"] = verified
     out.update(decide)
@@ -444,6 +501,29 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sharded_open_check(ctx, ab, rank, world, device, k):
+    """ShardedIpaOpen over NCCL at degree 2^k against the oracle's opening (both ways of passing h'); True on every rank
+    only if l_vec, r_vec, final_comm_key and c all agree"""
+    from accumulation_b200.sharded import ShardedIpaOpen, cyclic_shard
+    from oracle import cref
+    from tests.test_gpu_ipa_open import oracle_open, sponge_stand_in
+    from tests.test_gpu_sharded_open import _case
+    ok = True
+    for indexed in (True, False):
+        sf, key, h, xi0, hp, coeffs, z = _case(0, k, 500 + k)
+        shard = cyclic_shard(key, rank, world)
+        bases = ctx.register_bases(0, np.concatenate([shard, h.reshape(1, 8)]))
+        bases.precompute()
+        so = ShardedIpaOpen(ctx, 0, bases, k, rank=rank, world=world, hiding_index=shard.shape[0], device=device)
+        squeeze = sponge_stand_in(sf)
+        res = so.open(cyclic_shard(coeffs, rank, world), z, squeeze, h_prime_xy=None if indexed else hp, xi0_mont=xi0 if indexed else None)
+        el, er, efk, ec, _ = oracle_open(0, key, coeffs, z, hp, squeeze)
+        ok = ok and all(same_pt(x, y) for x, y in zip(res[0], el)) and all(same_pt(x, y) for x, y in zip(res[1], er))
+        ok = ok and np.array_equal(res[2], efk) and np.array_equal(res[3], ec)
+        bases.release()
+    return bool(ok)
 
 
 def ark_threads(n, omp_threads):

@@ -61,6 +61,10 @@ def num_threads() -> int:
     return lib().oracle_num_threads()
 
 
+def set_num_threads(n: int):
+    lib().oracle_set_num_threads(C.c_int(int(n)))
+
+
 def _binop(name, field, a, b):
     a, b = _u64(a), _u64(b)
     out = np.empty_like(a)

@@ -148,6 +148,9 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+/* threads of the following calls from this thread (torchrun exports OMP_NUM_THREADS=1 to every rank) */
+void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 
 /* ---------------------------------------------------------------- vector field ops */
 #define FE(p, i) ((const fe *)((p) + 4 * (i)))

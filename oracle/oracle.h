@@ -16,6 +16,7 @@ extern "C" {
  * Affine points: 8 x u64 = x[4] || y[4] (Montgomery) + separate infinity byte. */
 
 int  oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 /* field vectors (n elements each, Montgomery in / Montgomery out unless stated) */
 void oracle_fe_mul(int field, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);

@@ -12,6 +12,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_present():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a CPU-only box skips the gpu-marked tests instead of erroring.  When the gpu marker is
+    selected explicitly (`-m gpu`, what the driver runs on the B200 box) nothing is skipped: a missing device or a
+    missing libaccmsm.so must fail loudly there, never pass by skipping."""
+    if "gpu" in (config.getoption("-m") or "") or _cuda_present():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (no CPU path exists); run with -m gpu on the B200 box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def ctx():
     """One accmsm context on cuda:0.  Fails loudly (no skip, no CPU path) if the extension or GPU is missing."""

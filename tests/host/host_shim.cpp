@@ -28,6 +28,18 @@ extern "C" void host_fe_op(int field, int op, const uint32_t *a, const uint32_t 
     if (field == 0) binop<0>(op, a, b, o, n); else binop<1>(op, a, b, o, n);
 }
 
+template <int F> static void mul2op(int sub, const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *o, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fe_t x, y, z, w;
+        memcpy(x.l, a + 8 * i, 32); memcpy(y.l, b + 8 * i, 32); memcpy(z.l, c + 8 * i, 32); memcpy(w.l, d + 8 * i, 32);
+        fe_t r = sub ? Fp<F>::mul2sub(x, y, z, w) : Fp<F>::mul2(x, y, z, w);
+        memcpy(o + 8 * i, r.l, 32);
+    }
+}
+extern "C" void host_fe_mul2(int field, int sub, const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d, uint32_t *o, size_t n) {
+    if (field == 0) mul2op<0>(sub, a, b, c, d, o, n); else mul2op<1>(sub, a, b, c, d, o, n);
+}
+
 #include "../../accumulation_b200/csrc/ec.cuh"
 template <int C> static void ec_sum(const uint32_t *xy, const uint8_t *neg, size_t n, int mode, uint32_t *out_xy, uint8_t *out_inf) {
     using Cv = Curve<C>;

@@ -31,6 +31,14 @@ def fe_op(lib, field, code, a, b=None):
     return out
 
 
+def fe_mul2(lib, field, sub, a, b, c, d):
+    arrs = [np.ascontiguousarray(x, dtype=np.uint64) for x in (a, b, c, d)]
+    out = np.empty_like(arrs[0])
+    lib.host_fe_mul2(C.c_int(field), C.c_int(sub), *[x.ctypes.data_as(C.c_void_p) for x in arrs], out.ctypes.data_as(C.c_void_p),
+                     C.c_size_t(arrs[0].size // 4))
+    return out
+
+
 @pytest.mark.parametrize("field", [0, 1])
 def test_field_limb_algorithms(shim, field):
     m = [pyref.P_PALLAS_BASE, pyref.Q_PALLAS_SCALAR][field]
@@ -44,7 +52,12 @@ def test_field_limb_algorithms(shim, field):
     assert (fe_op(shim, field, 0, a, b) == cref.fe_mul(field, a, b)).all()
     assert (fe_op(shim, field, 1, a, b) == cref.fe_add(field, a, b)).all()
     assert (fe_op(shim, field, 2, a, b) == cref.fe_sub(field, a, b)).all()
-    assert (fe_op(shim, field, 3, a) == cref.fe_mul(field, a, a)).all()
+    assert (fe_op(shim, field, 3, a) == cref.fe_mul(field, a, a)).all()          # dedicated squaring (36 limb products)
+    # dual product with one reduction: a b + c d and a b - c d (the Y3 of every addition law in ec.cuh)
+    c, d = np.roll(a, 7, axis=0), np.roll(b, 13, axis=0)
+    ab, cd = cref.fe_mul(field, a, b), cref.fe_mul(field, c, d)
+    assert (fe_mul2(shim, field, 0, a, b, c, d) == cref.fe_add(field, ab, cd)).all()
+    assert (fe_mul2(shim, field, 1, a, b, c, d) == cref.fe_sub(field, ab, cd)).all()
     assert (fe_op(shim, field, 5, a) == cref.from_mont(field, a)).all()
     assert (fe_op(shim, field, 6, a) == cref.to_mont(field, a)).all()
     assert (fe_op(shim, field, 7, a) == cref.fe_sub(field, np.zeros_like(a), a)).all()
