@@ -63,20 +63,49 @@ def release_pinned(arr: np.ndarray):
 
 
 class Context:
-    """One accmsm_ctx bound to one GPU (one per process in the multi-GPU layout)."""
+    """One accmsm_ctx: bound to one GPU (`Context(0)`; one per process under torchrun) or to a group of GPUs of
+    one box (`Context(devices=[0, 1, ..])`, accmsm_init_multi): the same calls then shard keys by point range inside
+    the library."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices: Optional[Sequence[int]] = None, min_shard: Optional[int] = None):
         self._lib = load()
         h = C.c_void_p()
-        rc = self._lib.accmsm_init(C.byref(h), C.c_int(device))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.accmsm_init_multi(C.byref(h), arr, C.c_int(len(devices)))
+        else:
+            rc = self._lib.accmsm_init(C.byref(h), C.c_int(device))
         if rc != 0:
-            raise AccmsmError(f"accmsm_init(device={device}) failed: {self._lib.accmsm_strerror(rc).decode()} "
-                              "(a CUDA device is required; there is no CPU path)")
+            raise AccmsmError(f"accmsm_init(device={device if devices is None else list(devices)}) failed: "
+                              f"{self._lib.accmsm_strerror(rc).decode()} (a CUDA device is required; there is no CPU path)")
         self._h = h
+        self._owned = True
+        if min_shard is not None:
+            self.set_min_shard(min_shard)
+
+    @classmethod
+    def _borrowed(cls, lib, handle):
+        c = cls.__new__(cls)
+        c._lib, c._h, c._owned = lib, C.c_void_p(handle), False
+        return c
+
+    def device_count(self) -> int:
+        return int(self._lib.accmsm_device_count(self._h))
+
+    def device_ctx(self, index: int) -> "Context":
+        """the single-device ctx of device `index` of a group (for the device-pointer entry points); owned by the group"""
+        p = self._lib.accmsm_device_ctx(self._h, C.c_int(index))
+        if not p:
+            raise AccmsmError(f"device_ctx({index}): out of range")
+        return Context._borrowed(self._lib, p)
+
+    def set_min_shard(self, min_points: int):
+        self._check(self._lib.accmsm_set_min_shard(self._h, C.c_size_t(min_points)), "set_min_shard")
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.accmsm_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._lib.accmsm_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -57,7 +57,21 @@ void ipa_session_free(IpaSession *s);
 struct CsrSet;
 void csr_set_free(CsrSet *c);
 
+struct GroupWorker;
+struct GroupKey;
+struct GroupCsr;
+
 struct accmsm_ctx {
+    // ---- device group (accmsm_init_multi, multi_api.inc): a group ctx owns one child ctx per device, one host thread
+    //      per child, and no CUDA state of its own; every entry point below dispatches on !kids.empty()
+    std::vector<accmsm_ctx *> kids;
+    std::vector<GroupWorker *> workers;
+    std::unordered_map<uint64_t, GroupKey *> gkeys;
+    std::unordered_map<uint64_t, GroupCsr *> gcsrs;
+    std::unordered_map<uint64_t, uint64_t> gsessions;   // IpaPC::open sessions run on child 0: group id -> child session id
+    std::vector<char> peer_ok;                           // child g can store straight into child 0's memory
+    void *d_gather = nullptr;                            // on child 0's device: partial sums of all children, rank-major
+    size_t min_shard = size_t(1) << 16;                  // keys are cut into shards of at least this many points
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -605,9 +619,11 @@ const Bases *find_bases(accmsm_ctx *ctx, uint64_t handle) {
     return &it->second;
 }
 
-// MSM of host scalars, one vector.  d_extra/n_extra: XYZZ partials added before normalisation.
+// MSM of host scalars, one vector: uploads and enqueues on the ctx stream.  d_extra/n_extra: XYZZ partials added before
+// normalisation.  d_partial (nullable): where the un-normalised sum goes (DEVICE memory, possibly a peer GPU's);
+// normalise: the affine image goes to ctx->d_out_affine.  The caller fetches / synchronises.
 int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint64_t *scalars, int mont,
-                     const xyzz_t *d_extra, uint32_t n_extra, uint64_t out_xy[8], uint8_t *out_inf) {
+                     const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise) {
     cudaStream_t st = ctx->stream;
     clear_marks(ctx);
     CU(ctx, ctx->scalars.ensure(n * 32));
@@ -660,17 +676,93 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
             if (cudaEventRecord(ch.events[c], cs) != cudaSuccess) return ACCMSM_E_CUDA;
             return ACCMSM_OK;
         };
-        int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, nullptr, true, st, &ch);
+        int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, d_partial, normalise, st, &ch);
         if (rc) { ctx->last_error = "msm: chunked upload failed"; return rc; }
-        return fetch_affine(ctx, out_xy, out_inf, st);
+        return ACCMSM_OK;
     }
     { int urc = upload(ctx, ctx->scalars.p, scalars, bytes, st); if (urc) return urc; }
-    int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, nullptr, true, st);
-    if (rc) return rc;
-    return fetch_affine(ctx, out_xy, out_inf, st);
+    return msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, d_partial, normalise, st);
+}
+
+// identity partial(s) into d_out[0..k)
+template <int CURVE> void launch_identity_partials(accmsm_ctx *ctx, xyzz_t *d_out, uint32_t k, cudaStream_t st) {
+    k_finish<CURVE><<<k, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, d_out, nullptr, nullptr);
+    ctx->launches++;
+}
+
+// k scalar vectors from the host (k x n x 32 B) against bases [offset, offset + n), optional last pair
+// (base tail_index, tail[j]) per vector, as ONE pass per MAX_JOBS vectors; un-normalised sums -> d_partials[0..k)
+// and/or affine images -> host.  Enqueues on the ctx stream and synchronises.
+int msm_rows_host(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, size_t k, const uint64_t *scalars, int mont,
+                  size_t tail_index, const uint64_t *tail_scalars, xyzz_t *d_partials, uint64_t *out_xy, uint8_t *out_inf) {
+    cudaStream_t st = ctx->stream;
+    const bool tail = tail_scalars != nullptr;
+    const size_t n_eff = n + (tail ? 1 : 0), row = n_eff * 32;
+    clear_marks(ctx);
+    if (n_eff == 0) {
+        if (d_partials) { if (B.curve == 0) launch_identity_partials<0>(ctx, d_partials, (uint32_t)k, st); else launch_identity_partials<1>(ctx, d_partials, (uint32_t)k, st); }
+        if (out_xy) for (size_t j = 0; j < k; j++) write_identity(ctx, B.curve, out_xy + 8 * j, out_inf + j);
+        CU(ctx, cudaStreamSynchronize(st));
+        return ACCMSM_OK;
+    }
+    CU(ctx, ctx->scalars.ensure(k * row));
+    mark(ctx, ST_H2D, st);
+    if (!tail) { int urc = upload(ctx, ctx->scalars.p, scalars, k * row, st); if (urc) return urc; }
+    else for (size_t j = 0; j < k; j++) {
+        if (n) { int urc = upload(ctx, ctx->scalars.p + j * row, scalars + j * n * 4, n * 32, st); if (urc) return urc; }
+        { int urc = upload_small(ctx, ctx->scalars.p + j * row + n * 32, tail_scalars + 4 * j, 32, st); if (urc) return urc; }
+    }
+    for (size_t j0 = 0; j0 < k; j0 += MAX_JOBS) {
+        MsmJobs jobs;
+        jobs.njobs = (uint32_t)std::min<size_t>(MAX_JOBS, k - j0);
+        if (tail) jobs.tail_base = (uint32_t)tail_index;
+        const uint8_t *ptrs[MAX_JOBS];
+        for (uint32_t j = 0; j < jobs.njobs; j++) { jobs.offset[j] = offset; ptrs[j] = ctx->scalars.p + (j0 + j) * row; }
+        int rc = msm_mem(ctx, B, jobs, n_eff, ptrs, mont, nullptr, 0, d_partials ? d_partials + j0 : nullptr, out_xy != nullptr, st);
+        if (rc) return rc;
+        if (out_xy) {
+            mark(ctx, ST_D2H, st);
+            CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, jobs.njobs * 64, cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaMemcpyAsync(ctx->h_out + 8 * MAX_JOBS, ctx->d_out_inf, jobs.njobs * 4, cudaMemcpyDeviceToHost, st));
+            mark(ctx, ST_COUNT, st);
+            CU(ctx, cudaStreamSynchronize(st));
+            memcpy(out_xy + 8 * j0, ctx->h_out, jobs.njobs * 64);
+            const uint32_t *inf = (const uint32_t *)(ctx->h_out + 8 * MAX_JOBS);
+            for (uint32_t j = 0; j < jobs.njobs; j++) out_inf[j0 + j] = inf[j] != 0;
+        }
+    }
+    if (!out_xy) { mark(ctx, ST_COUNT, st); CU(ctx, cudaStreamSynchronize(st)); }
+    collect_timings(ctx);
+    return ACCMSM_OK;
 }
 
 }  // namespace
+
+// ---- device-group layer (multi_api.inc): the same entry points over a key sharded by point range across GPUs
+int group_destroy(accmsm_ctx *g);
+int group_register_bases(accmsm_ctx *g, int curve, const uint64_t *xy, const uint8_t *infinity, size_t n, uint64_t seed,
+                         uint64_t first_index, bool synthetic, uint64_t *handle);
+int group_release_bases(accmsm_ctx *g, uint64_t handle);
+int group_precompute(accmsm_ctx *g, uint64_t handle, int window_bits);
+int group_download_bases(accmsm_ctx *g, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out);
+int group_msm_rows(accmsm_ctx *g, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars, int mont,
+                   bool has_tail, size_t tail_index, const uint64_t *tail_scalars, uint64_t *out_xy, uint8_t *out_inf);
+int group_ipa_final_key(accmsm_ctx *g, uint64_t handle, const uint64_t *challenges_mont, int k, uint64_t out_xy[8], uint8_t *out_inf);
+int group_hp_decide(accmsm_ctx *g, uint64_t handle, const uint64_t *a_mont, const uint64_t *b_mont, size_t n, size_t hiding_index,
+                    const uint64_t *randomness_mont, uint64_t *xy, uint8_t *inf);
+int group_hp_product_poly_comm(accmsm_ctx *g, uint64_t handle, const uint64_t *const *a_vecs, const size_t *a_lens,
+                               const uint64_t *const *b_vecs, const size_t *b_lens, int n_in, const uint64_t *mu, size_t len,
+                               const uint64_t *hiding_a, size_t n_ha, const uint64_t *hiding_b, size_t n_hb, uint64_t *out_low_xy,
+                               uint8_t *out_low_inf, uint64_t *out_high_xy, uint8_t *out_high_inf, uint64_t *out_tvecs);
+int group_register_csr(accmsm_ctx *g, int field, int n_mats, const uint32_t *const *row_ptr, const uint32_t *const *cols,
+                       const uint64_t *const *coeffs_mont, size_t n_rows, uint64_t *handle);
+int group_release_csr(accmsm_ctx *g, uint64_t handle);
+int group_csr_matvec_commit(accmsm_ctx *g, uint64_t key_handle, uint64_t csr_handle, const uint64_t *input, size_t n_input,
+                            const uint64_t *witness, size_t n_witness, size_t hiding_index, const uint64_t *blinders_mont,
+                            uint64_t *const *out_vecs, uint64_t *out_xy, uint8_t *out_inf);
+int group_open_key(accmsm_ctx *g, uint64_t handle, uint64_t *kid0_handle);     // full key on child 0 for IpaPC::open sessions
+inline bool is_group(const accmsm_ctx *ctx) { return ctx && !ctx->kids.empty(); }
+#define GROUP_NO_DEV(ctx, name) do { if (is_group(ctx)) return fail_arg(ctx, name ": device-pointer entry points need a single-device ctx (accmsm_device_ctx)"); } while (0)
 
 // =====================================================================================================
 // C-ABI
@@ -740,6 +832,7 @@ int accmsm_init(accmsm_ctx **out, int device) {
 
 void accmsm_destroy(accmsm_ctx *ctx) {
     if (!ctx) return;
+    if (is_group(ctx)) { group_destroy(ctx); return; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->bases) {
@@ -784,6 +877,7 @@ void accmsm_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int accmsm_set_window_bits(accmsm_ctx *ctx, int c) {
     if (!ctx || c < 0 || c > 16 || c == 1) return fail_arg(ctx, "window bits must be 0 (auto) or 2..16");
+    for (accmsm_ctx *kid : ctx->kids) kid->window_bits = c;
     ctx->window_bits = c;
     return ACCMSM_OK;
 }
@@ -791,16 +885,31 @@ int accmsm_set_window_bits(accmsm_ctx *ctx, int c) {
 int accmsm_set_ipa_fold(accmsm_ctx *ctx, int rounds, int min_log_n) {
     if (!ctx || rounds < 0 || rounds > 10 || min_log_n < 0 || min_log_n > 31)
         return fail_arg(ctx, "set_ipa_fold: rounds must be 0 (never) or 1..10, min_log_n 0..31");
+    for (accmsm_ctx *kid : ctx->kids) accmsm_set_ipa_fold(kid, rounds, min_log_n);
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->ipa_fold_rounds = rounds; ctx->ipa_fold_min_log = min_log_n;
     return ACCMSM_OK;
 }
 
-uint64_t accmsm_kernel_launches(accmsm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t accmsm_kernel_launches(accmsm_ctx *ctx) {
+    if (!ctx) return 0;
+    uint64_t total = ctx->launches;
+    for (accmsm_ctx *kid : ctx->kids) total += kid->launches;
+    return total;
+}
 
 int accmsm_last_timings(accmsm_ctx *ctx, float *ms_out, int max_stages) {
     if (!ctx || !ms_out) return ACCMSM_E_ARG;
     int k = std::min<int>(max_stages, ST_COUNT);
+    if (is_group(ctx)) {        // per stage: the slowest child (the children run concurrently)
+        for (int i = 0; i < k; i++) ms_out[i] = 0.f;
+        float tmp[ST_COUNT];
+        for (accmsm_ctx *kid : ctx->kids) {
+            accmsm_last_timings(kid, tmp, k);
+            for (int i = 0; i < k; i++) ms_out[i] = std::max(ms_out[i], tmp[i]);
+        }
+        return k;
+    }
     // calls that only enqueued on a caller stream are collected here, once the caller has synchronised
     std::lock_guard<std::mutex> lock(ctx->mu);
     collect_timings(ctx);
@@ -811,6 +920,7 @@ int accmsm_last_timings(accmsm_ctx *ctx, float *ms_out, int max_stages) {
 int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const uint8_t *infinity, size_t n,
                           uint64_t *handle) {
     if (!ctx || !handle || (curve != 0 && curve != 1) || (n && !xy)) return fail_arg(ctx, "register_bases: bad argument");
+    if (is_group(ctx)) return group_register_bases(ctx, curve, xy, infinity, n, 0, 0, false, handle);
     if (n >= (size_t(1) << 31)) return fail_arg(ctx, "register_bases: n must be < 2^31");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
@@ -833,6 +943,7 @@ int accmsm_register_bases(accmsm_ctx *ctx, int curve, const uint64_t *xy, const 
 int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, uint64_t first_index, size_t n,
                                     uint64_t *handle) {
     if (!ctx || !handle || (curve != 0 && curve != 1)) return fail_arg(ctx, "register_synthetic_bases: bad argument");
+    if (is_group(ctx)) return group_register_bases(ctx, curve, nullptr, nullptr, n, seed, first_index, true, handle);
     if (n >= (size_t(1) << 31)) return fail_arg(ctx, "register_synthetic_bases: n must be < 2^31");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
@@ -855,6 +966,7 @@ int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, u
 int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
     if (!ctx || window_bits < 0 || (window_bits && (window_bits < 4 || window_bits > 21)))
         return fail_arg(ctx, "precompute_bases: window bits must be 0 (auto) or 4..21");
+    if (is_group(ctx)) return group_precompute(ctx, handle, window_bits);
     std::lock_guard<std::mutex> lock(ctx->mu);
     auto it = ctx->bases.find(handle);
     if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }
@@ -864,6 +976,7 @@ int accmsm_precompute_bases(accmsm_ctx *ctx, uint64_t handle, int window_bits) {
 
 int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out) {
     if (!ctx || (n && !xy_out)) return fail_arg(ctx, "download_bases: bad argument");
+    if (is_group(ctx)) return group_download_bases(ctx, handle, offset, n, xy_out);
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
@@ -876,6 +989,7 @@ int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_
 
 int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle) {
     if (!ctx) return ACCMSM_E_ARG;
+    if (is_group(ctx)) return group_release_bases(ctx, handle);
     std::lock_guard<std::mutex> lock(ctx->mu);
     auto it = ctx->bases.find(handle);
     if (it == ctx->bases.end()) { ctx->last_error = "unknown bases handle"; return ACCMSM_E_HANDLE; }
@@ -891,13 +1005,16 @@ int accmsm_release_bases(accmsm_ctx *ctx, uint64_t handle) {
 int accmsm_msm(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const uint64_t *scalars,
                int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf) {
     if (!ctx || !out_xy || !out_inf || (n && !scalars)) return fail_arg(ctx, "msm: bad argument");
+    if (is_group(ctx)) return group_msm_rows(ctx, handle, offset, n, 1, scalars, scalars_montgomery, false, 0, nullptr, out_xy, out_inf);
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
     if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "msm: range exceeds registered bases");
     if (n == 0) return write_identity(ctx, B->curve, out_xy, out_inf);
     CU(ctx, cudaSetDevice(ctx->device));
-    return msm_host_scalars(ctx, *B, offset, n, scalars, scalars_montgomery, nullptr, 0, out_xy, out_inf);
+    int rc = msm_host_scalars(ctx, *B, offset, n, scalars, scalars_montgomery, nullptr, 0, nullptr, true);
+    if (rc) return rc;
+    return fetch_affine(ctx, out_xy, out_inf, ctx->stream);
 }
 
 // VariableBaseMSM::multi_scalar_mul(&bases, &scalars) for bases that are not a registered key (the literal ark-ec
@@ -907,6 +1024,7 @@ int accmsm_msm_oneshot(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, con
                        int scalars_montgomery, size_t n, uint64_t out_xy[8], uint8_t *out_inf) {
     if (!ctx || !out_xy || !out_inf || (curve != 0 && curve != 1) || (n && (!bases_xy || !scalars)) || n >= (size_t(1) << 31))
         return fail_arg(ctx, "msm_oneshot: bad argument");
+    if (is_group(ctx)) return accmsm_msm_oneshot(ctx->kids[0], curve, bases_xy, infinity, scalars, scalars_montgomery, n, out_xy, out_inf);
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return write_identity(ctx, curve, out_xy, out_inf);
     CU(ctx, cudaSetDevice(ctx->device));
@@ -934,66 +1052,36 @@ int accmsm_msm_oneshot(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, con
 int accmsm_msm_batch(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars,
                      int scalars_montgomery, uint64_t *out_xy, uint8_t *out_inf) {
     if (!ctx || (k && (!out_xy || !out_inf)) || (n && k && !scalars)) return fail_arg(ctx, "msm_batch: bad argument");
+    if (is_group(ctx)) return group_msm_rows(ctx, handle, offset, n, k, scalars, scalars_montgomery, false, 0, nullptr, out_xy, out_inf);
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
     if (offset > B->n || n > B->n - offset) return fail_arg(ctx, "msm_batch: range exceeds registered bases");
     if (n == 0) { for (size_t j = 0; j < k; j++) write_identity(ctx, B->curve, out_xy + 8 * j, out_inf + j); return ACCMSM_OK; }
     CU(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     // all k scalar vectors go up in one copy; groups of MAX_JOBS share one pass of the pipeline (one sort,
     // one accumulation over all their bucket sets, one reduction, one finish launch)
-    clear_marks(ctx);
-    CU(ctx, ctx->scalars.ensure(n * k * 32));
-    mark(ctx, ST_H2D, st);
-    { int urc = upload(ctx, ctx->scalars.p, scalars, n * k * 32, st); if (urc) return urc; }
-    for (size_t j0 = 0; j0 < k; j0 += MAX_JOBS) {
-        MsmJobs jobs;
-        jobs.njobs = (uint32_t)std::min<size_t>(MAX_JOBS, k - j0);
-        const uint8_t *ptrs[MAX_JOBS];
-        for (uint32_t j = 0; j < jobs.njobs; j++) { jobs.offset[j] = offset; ptrs[j] = ctx->scalars.p + (j0 + j) * n * 32; }
-        int rc = msm_mem(ctx, *B, jobs, n, ptrs, scalars_montgomery, nullptr, 0, nullptr, true, st);
-        if (rc) return rc;
-        mark(ctx, ST_D2H, st);
-        CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, jobs.njobs * 64, cudaMemcpyDeviceToHost, st));
-        CU(ctx, cudaMemcpyAsync(ctx->h_out + 8 * MAX_JOBS, ctx->d_out_inf, jobs.njobs * 4, cudaMemcpyDeviceToHost, st));
-        mark(ctx, ST_COUNT, st);
-        CU(ctx, cudaStreamSynchronize(st));
-        memcpy(out_xy + 8 * j0, ctx->h_out, jobs.njobs * 64);
-        const uint32_t *inf = (const uint32_t *)(ctx->h_out + 8 * MAX_JOBS);
-        for (uint32_t j = 0; j < jobs.njobs; j++) out_inf[j0 + j] = inf[j] != 0;
-    }
-    collect_timings(ctx);
-    return ACCMSM_OK;
+    return msm_rows_host(ctx, *B, offset, n, k, scalars, scalars_montgomery, 0, nullptr, nullptr, out_xy, out_inf);
 }
 
 int accmsm_commit(accmsm_ctx *ctx, uint64_t handle, size_t n, const uint64_t *elems_mont, size_t hiding_index,
                   const uint64_t *randomizer_mont, uint64_t out_xy[8], uint8_t *out_inf) {
     if (!ctx || !out_xy || !out_inf || (n && !elems_mont)) return fail_arg(ctx, "commit: bad argument");
     if (!randomizer_mont) return accmsm_msm(ctx, handle, 0, n, elems_mont, 1, out_xy, out_inf);
+    if (is_group(ctx)) return group_msm_rows(ctx, handle, 0, n, 1, elems_mont, 1, true, hiding_index, randomizer_mont, out_xy, out_inf);
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
     if (n > B->n || hiding_index >= B->n) return fail_arg(ctx, "commit: range exceeds registered bases");
     CU(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     // one pass over n + 1 pairs: the elements against the generators, then (hiding generator, randomizer)
-    clear_marks(ctx);
-    CU(ctx, ctx->scalars.ensure((n + 1) * 32));
-    mark(ctx, ST_H2D, st);
-    if (n) { int urc = upload(ctx, ctx->scalars.p, elems_mont, n * 32, st); if (urc) return urc; }
-    { int urc = upload_small(ctx, ctx->scalars.p + n * 32, randomizer_mont, 32, st); if (urc) return urc; }
-    MsmJobs jobs(0);
-    jobs.tail_base = (uint32_t)hiding_index;
-    const uint8_t *ptr = ctx->scalars.p;
-    int rc = msm_mem(ctx, *B, jobs, n + 1, &ptr, 1, nullptr, 0, nullptr, true, st);
-    if (rc) return rc;
-    return fetch_affine(ctx, out_xy, out_inf, st);
+    return msm_rows_host(ctx, *B, 0, n, 1, elems_mont, 1, hiding_index, randomizer_mont, nullptr, out_xy, out_inf);
 }
 
 int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
                    int scalars_montgomery, uint64_t out_xy[8], uint8_t *out_inf, void *stream) {
     if (!ctx || !out_xy || !out_inf || (n && !d_scalars)) return fail_arg(ctx, "msm_dev: bad argument");
+    GROUP_NO_DEV(ctx, "msm_dev");
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
@@ -1010,6 +1098,7 @@ int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, co
 int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const void *d_scalars,
                            int scalars_montgomery, void *d_out_partial, void *stream) {
     if (!ctx || !d_out_partial || (n && !d_scalars)) return fail_arg(ctx, "msm_partial_dev: bad argument");
+    GROUP_NO_DEV(ctx, "msm_partial_dev");
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
@@ -1033,9 +1122,33 @@ int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size
     return ACCMSM_OK;
 }
 
+// k scalar vectors from HOST memory against bases [offset, offset + n); optional last pair (base tail_index,
+// tail_scalars[j]) per vector; the k un-normalised sums go to d_out_partials (DEVICE memory, k x 16 u64, possibly a peer
+// GPU's).  One GPU's share of msm / msm_batch / commit when the key is sharded by point range.  Blocking.
+int accmsm_msm_partial(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars,
+                       int scalars_montgomery, size_t tail_index, const uint64_t *tail_scalars, void *d_out_partials) {
+    if (!ctx || is_group(ctx) || !d_out_partials || k == 0 || (n && !scalars)) return fail_arg(ctx, "msm_partial: bad argument");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const Bases *B = find_bases(ctx, handle);
+    if (!B) return ACCMSM_E_HANDLE;
+    if (offset > B->n || n > B->n - offset || (tail_scalars && tail_index >= B->n)) return fail_arg(ctx, "msm_partial: range exceeds registered bases");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (k == 1 && !tail_scalars && n) {       // the single-vector path overlaps the digit kernel with a chunked upload
+        clear_marks(ctx);
+        int rc = msm_host_scalars(ctx, *B, offset, n, scalars, scalars_montgomery, nullptr, 0, (xyzz_t *)d_out_partials, false);
+        if (rc) return rc;
+        mark(ctx, ST_COUNT, ctx->stream);
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        collect_timings(ctx);
+        return ACCMSM_OK;
+    }
+    return msm_rows_host(ctx, *B, offset, n, k, scalars, scalars_montgomery, tail_index, tail_scalars, (xyzz_t *)d_out_partials, nullptr, nullptr);
+}
+
 int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k, uint64_t out_xy[8],
                                 uint8_t *out_inf, void *stream) {
     if (!ctx || !out_xy || !out_inf || (k && !d_partials) || (curve != 0 && curve != 1)) return fail_arg(ctx, "combine_partials: bad argument");
+    GROUP_NO_DEV(ctx, "combine_partials_dev");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -1052,6 +1165,7 @@ int accmsm_combine_partials_batch_dev(accmsm_ctx *ctx, int curve, const void *d_
                                       uint8_t *out_inf, void *stream) {
     if (!ctx || !out_xy || !out_inf || !d_partials || k == 0 || m == 0 || m > MAX_JOBS || (curve != 0 && curve != 1))
         return fail_arg(ctx, "combine_partials_batch: bad argument");
+    GROUP_NO_DEV(ctx, "combine_partials_batch_dev");
     std::lock_guard<std::mutex> lock(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -1081,6 +1195,7 @@ static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_m
 int accmsm_ipa_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k, uint64_t out_xy[8],
                          uint8_t *out_inf) {
     if (!ctx || !out_xy || !out_inf || (k && !challenges_mont) || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key: bad argument");
+    if (is_group(ctx)) return group_ipa_final_key(ctx, handle, challenges_mont, k, out_xy, out_inf);
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
@@ -1111,6 +1226,7 @@ int accmsm_ipa_check_final_key(accmsm_ctx *ctx, uint64_t handle, const uint64_t 
 int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uint64_t *challenges_mont, int k,
                                      size_t coeff_offset, size_t n, void *d_out_partial, void *stream) {
     if (!ctx || !d_out_partial || (k && !challenges_mont) || k < 0 || k > 30) return fail_arg(ctx, "ipa_final_key_partial_dev: bad argument");
+    GROUP_NO_DEV(ctx, "ipa_final_key_partial_dev");
     std::lock_guard<std::mutex> lock(ctx->mu);
     const Bases *B = find_bases(ctx, handle);
     if (!B) return ACCMSM_E_HANDLE;
@@ -1130,3 +1246,4 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
 #include "vec_api.inc"
 #include "ipa_api.inc"
 #include "fused_api.inc"
+#include "multi_api.inc"

@@ -119,6 +119,14 @@ static __constant__ uint32_t ACC_OPAQUE_ZERO;
 #ifndef ACC_MUL_SHIFT_TOP
 #define ACC_MUL_SHIFT_TOP 0
 #endif
+// ACC_SQR_DEDICATED = 1: Fp::sqr skips the symmetric limb products (36 instead of 64 IMAD.WIDE; the skipped ones become
+// carry ripples on the ALU pipe).  In isolation that loses (tools/ubench2.cu, profiles/r02a_ubench2.jsonl: 73.7 G
+// squarings/s against 78.8 G products/s at 16 warps per SM -- the part is power-limited under pure multiplier load), but
+// inside k_accumulate, where the multiplier pipe is the busiest unit and the ALU pipe has slack, it wins: 2.109 vs
+// 2.163 ms at 2^20 points (same box, same run, profiles/r02b_bench*.jsonl).  ON.
+#ifndef ACC_SQR_DEDICATED
+#define ACC_SQR_DEDICATED 1
+#endif
 #ifndef ACC_MUL_WIDE_RIPPLES
 #define ACC_MUL_WIDE_RIPPLES 0
 #endif
@@ -286,6 +294,9 @@ template <int FIELD> struct Fp {
     // products, same reduction.  Bounds: the row operand is < 2a, so V < 2a + m < 2^256 after every round and the result
     // is < a^2 / R + m < 2m.
     static ACC_HD fe_t sqr(const fe_t &A) {
+#if !ACC_SQR_DEDICATED
+        return mul(A, A);
+#endif
         const uint32_t *a = A.l;
         uint32_t d[8], s[8];      // d = 2a, s[j] = a[j] << 1 (d[j] with the bit shifted in from limb j - 1 cleared)
         d[0] = s[0] = a[0] << 1;

@@ -51,6 +51,12 @@ public:
         int rc = accmsm_init(&ctx_, device);
         if (rc) throw AccmsmError(std::string("accmsm_init: ") + accmsm_strerror(rc) + " (a CUDA device is required; there is no CPU path)");
     }
+    // a group of GPUs behind the same calls (accmsm_init_multi): keys are sharded by point range inside the library
+    explicit Context(const std::vector<int> &devices, size_t min_shard = size_t(1) << 16) {
+        int rc = accmsm_init_multi(&ctx_, devices.data(), (int)devices.size());
+        if (rc) throw AccmsmError(std::string("accmsm_init_multi: ") + accmsm_strerror(rc) + " (a CUDA device is required; there is no CPU path)");
+        accmsm_set_min_shard(ctx_, min_shard);
+    }
     ~Context() { accmsm_destroy(ctx_); }
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;

@@ -15,9 +15,15 @@
  *   curve id      : 0 = Pallas (coordinates Fp, scalars Fq), 1 = Vesta (coordinates Fq, scalars Fp)
  *   field id      : 0 = Fp (Pallas base), 1 = Fq (Pallas scalar)
  *
- * Every call is blocking and returns 0 or a negative ACCMSM_E_* code; nothing throws or aborts.
+ * Every call returns 0 or a negative ACCMSM_E_* code; nothing throws or aborts.  Calls are blocking, with one documented
+ * exception: the `*_dev` entry points that take a `stream` argument only ENQUEUE when that argument is not NULL (the caller
+ * synchronises its stream).  The ctx has one workspace; work left in flight by such a call is ordered before every later
+ * call on any stream by an event, so interleaving streams is safe.  Small host arguments (challenges, randomizers) are
+ * copied before the call returns: the caller may reuse its buffers immediately, page-locked or not.
  * There is no CPU fallback: without a CUDA device accmsm_init fails with ACCMSM_E_CUDA.
- * A ctx is bound to one GPU and serialises its calls internally (one ctx per GPU per process).
+ * A ctx is bound to one GPU (accmsm_init) or to a group of GPUs of one box (accmsm_init_multi) and serialises its calls
+ * internally.  Limits: a registered key has < 2^31 bases, and jobs x windows x n < 2^31 per MSM pass (n < 2^27 at the
+ * automatic window sizes).
  */
 #ifndef ACCMSM_H
 #define ACCMSM_H
@@ -39,6 +45,23 @@ enum {
 
 /* ---- context ------------------------------------------------------------------------------------ */
 int  accmsm_init(accmsm_ctx **out, int device);
+/* One ctx over the GPUs devices[0 .. n_dev) of this box: one host thread and one stream set per device
+ * inside the library.  Every HOST-pointer entry point of this header then spans the devices with no change on the caller's
+ * side: accmsm_register_bases cuts the key into contiguous point ranges (one per GPU, at least accmsm_set_min_shard points
+ * each), each GPU uploads ITS slice of the caller's scalar / vector buffers over its own PCIe link, runs the whole pipeline
+ * on its range and stores one un-normalised 128-byte partial per result into device 0's memory over NVLink (peer store from
+ * the last kernel; cudaMemcpyPeer without peer access); device 0 adds them and normalises.  accmsm_ipa_final_key expands
+ * h(X) per range with no exchange; accmsm_hp_decide / accmsm_hp_product_poly_comm / accmsm_csr_matvec_commit and the
+ * element-wise accmsm_vec_* calls shard by the same index ranges (CSR rows with z replicated).  IpaPC::open sessions run on
+ * device 0 over a copy of the whole key assembled by peer copies.  The device-pointer (`*_dev`) entry points need a
+ * single-device ctx: accmsm_device_ctx(group, i).  This is what the single-process Rust callers
+ * (src/ipa_pc_as/mod.rs:836-845, src/hp_as/mod.rs:910-918, src/r1cs_nark_as/mod.rs:1052-1097) bind. */
+int  accmsm_init_multi(accmsm_ctx **out, const int *devices, int n_dev);
+int  accmsm_device_count(accmsm_ctx *ctx);
+accmsm_ctx *accmsm_device_ctx(accmsm_ctx *ctx, int index);      /* owned by the group; NULL when out of range */
+/* keys (vectors, rows) are cut into shards of at least min_points elements; 0 = always use every device.  Default 2^16:
+ * below that the fixed tail of an MSM outweighs the split. */
+int  accmsm_set_min_shard(accmsm_ctx *ctx, size_t min_points);
 void accmsm_destroy(accmsm_ctx *ctx);
 const char *accmsm_strerror(int code);
 const char *accmsm_last_error(accmsm_ctx *ctx);
@@ -122,6 +145,13 @@ int accmsm_msm_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, co
 int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n,
                            const void *d_scalars, int scalars_montgomery, void *d_out_partial,
                            void *stream);
+/* One GPU's share of accmsm_msm / accmsm_msm_batch / accmsm_commit over a key sharded by point range: k scalar vectors
+ * from HOST memory (k x n x 4 u64) against bases [offset, offset + n) of this GPU's handle, optionally a last pair
+ * (base tail_index, tail_scalars[j]) per vector (the hiding term of PedersenCommitment::commit, on the shard that owns the
+ * hiding generator; tail_scalars in the same representation as scalars, NULL = none).  The k un-normalised sums go to
+ * d_out_partials: DEVICE memory, k x 16 u64, possibly on a peer GPU (the final kernel stores there directly).  Blocking. */
+int accmsm_msm_partial(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars,
+                       int scalars_montgomery, size_t tail_index, const uint64_t *tail_scalars, void *d_out_partials);
 /* Sum k gathered partials (DEVICE, k x 16 u64) and normalise: the G-way add after the NCCL gather.
  * Enqueued on `stream` (NULL = the ctx stream); blocks until the affine result is on the host. */
 int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partials, size_t k,
@@ -235,6 +265,12 @@ int accmsm_csr_matvec(accmsm_ctx *ctx, int field, int n_mats, const uint32_t *co
 int accmsm_hp_decide(accmsm_ctx *ctx, uint64_t handle, const uint64_t *a_mont, const uint64_t *b_mont, size_t n,
                      size_t hiding_index, const uint64_t *randomness_mont, const uint64_t *expected_xy,
                      const uint8_t *expected_inf, int *accept, uint64_t *out_xy, uint8_t *out_inf);
+/* One GPU's share of the same decision when the key is sharded by point range: a, b are THIS shard's
+ * slices (n elements against bases [0, n) of `handle`), the product is formed on the device, and the three un-normalised
+ * partial commitments go to d_out_partials (DEVICE memory, 3 x 16 u64, possibly a peer GPU's), to be summed with
+ * accmsm_combine_partials_batch_dev.  randomness_mont != NULL only on the shard owning the hiding generator. */
+int accmsm_hp_decide_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uint64_t *a_mont, const uint64_t *b_mont, size_t n,
+                                 size_t hiding_index, const uint64_t *randomness_mont, void *d_out_partials);
 /* compute_t_vecs + compute_product_poly_comm (src/hp_as/mod.rs:288-388): all t-vectors except the middle one are
  * committed (no randomiser).  out_low / out_high: (n_in - 1) x 8; out_tvecs (nullable): (2 n_in - 1) x len x 4. */
 int accmsm_hp_product_poly_comm(accmsm_ctx *ctx, uint64_t handle, const uint64_t *const *a_vecs, const size_t *a_lens,
@@ -242,6 +278,12 @@ int accmsm_hp_product_poly_comm(accmsm_ctx *ctx, uint64_t handle, const uint64_t
                                 size_t len, const uint64_t *hiding_a, size_t n_ha, const uint64_t *hiding_b, size_t n_hb,
                                 uint64_t *out_low_xy, uint8_t *out_low_inf, uint64_t *out_high_xy, uint8_t *out_high_inf,
                                 uint64_t *out_tvecs);
+/* sharded form: the vectors are this shard's slices; 2 n_in - 2 partials (low rows, then high) -> d_out_partials (DEVICE);
+ * row r of the t-vectors (nullable) is written at out_tvecs + r * tvec_row_stride * 4 */
+int accmsm_hp_product_poly_comm_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uint64_t *const *a_vecs, const size_t *a_lens,
+                                            const uint64_t *const *b_vecs, const size_t *b_lens, int n_in, const uint64_t *mu,
+                                            size_t len, const uint64_t *hiding_a, size_t n_ha, const uint64_t *hiding_b, size_t n_hb,
+                                            void *d_out_partials, uint64_t *out_tvecs, size_t tvec_row_stride);
 /* R1CS matrices registered once (fixed from index time on: src/r1cs_nark_as/r1cs_nark/mod.rs:78-124); then
  * t_M = M (input || witness) and comm_M = Commit(t_M, blinder_M) for all matrices in one call
  * (prover :183-185 + :216-218, verifier :356-361 + :375-389, AS decider src/r1cs_nark_as/mod.rs:1052-1097).
@@ -252,6 +294,14 @@ int accmsm_release_csr(accmsm_ctx *ctx, uint64_t handle);
 int accmsm_csr_matvec_commit(accmsm_ctx *ctx, uint64_t key_handle, uint64_t csr_handle, const uint64_t *input, size_t n_input,
                              const uint64_t *witness, size_t n_witness, size_t hiding_index, const uint64_t *blinders_mont,
                              uint64_t *const *out_vecs, uint64_t *out_xy, uint8_t *out_inf);
+
+/* One GPU's share of the same step when the key -- and with it the rows of the matrices -- is sharded by point range
+ * (SURVEY.md 8e, K5): csr_handle holds THIS shard's rows, z = input || witness is replicated, the n_mats un-normalised partial
+ * commitments go to d_out_partials (DEVICE memory, possibly a peer GPU's); blinders_mont != NULL only on the shard that owns
+ * the hiding generator; out_vecs[m] receive this shard's rows of t_M. */
+int accmsm_csr_matvec_commit_partial_dev(accmsm_ctx *ctx, uint64_t key_handle, uint64_t csr_handle, const uint64_t *input, size_t n_input,
+                                         const uint64_t *witness, size_t n_witness, size_t hiding_index, const uint64_t *blinders_mont,
+                                         uint64_t *const *out_vecs, void *d_out_partials);
 
 #ifdef __cplusplus
 }

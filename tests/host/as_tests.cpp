@@ -39,8 +39,18 @@ static Affine oracle_commit_(int curve, const std::vector<Affine> &gens, const s
 }
 
 int main() {
+    // ACCMSM_TEST_DEVICES="0,0" (or "0,1"): the same scenarios on a device-group ctx (accmsm_init_multi), keys sharded
+    // by point range inside the library
     std::shared_ptr<Context> ctx;
-    try { ctx = std::make_shared<Context>(0); }
+    try {
+        const char *devs = getenv("ACCMSM_TEST_DEVICES");
+        if (devs && *devs) {
+            std::vector<int> d;
+            for (const char *p = devs; *p;) { d.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p == ',') p++; }
+            ctx = std::make_shared<Context>(d, 16);
+            printf("device group of %d\n", accmsm_device_count(ctx->raw()));
+        } else ctx = std::make_shared<Context>(0);
+    }
     catch (const AccmsmError &e) { std::printf("NO_GPU %s\n", e.what()); return 3; }   // no CPU fallback: refuse to run
 
     for (int curve = 0; curve < 2; curve++) {

@@ -34,9 +34,11 @@ def test_harness_builds_and_refuses_without_gpu():
 
 
 @pytest.mark.gpu
-def test_cpp_harness_scenarios():
+@pytest.mark.parametrize("devices", ["", "0,0"] + (["0,1"] if os.environ.get("ACCMSM_HAVE_2_GPUS") else []))
+def test_cpp_harness_scenarios(devices):
+    """devices = "0,0": the same scenarios through a 2-device group ctx (accmsm_init_multi; virtual shards on one GPU)"""
     exe = build_harness()
-    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, ACCMSM_TEST_DEVICES=devices))
     print(p.stdout[-4000:])
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "FAIL" not in p.stdout and p.stdout.count("PASS") >= 40
