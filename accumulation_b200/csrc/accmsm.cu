@@ -14,6 +14,7 @@
 
 #include "../../include/accmsm.h"
 #include "msm.cuh"
+#include "sort.cuh"
 #include "vec.cuh"
 #include "ipa.cuh"
 
@@ -91,6 +92,11 @@ struct accmsm_ctx {
     DevBuf<uint32_t> digits, hist, offsets, cursor, entries, cta_ids, tile_sums, tile_offs;
     DevBuf<xyzz_t> buckets, red_sum[2], red_wsum[2], cta_parts, partial;
     DevBuf<uint8_t> scalars, misc;
+    DevBuf<uint2> sort_pairs;                                   // sort.cuh: (key low bits, entry) pairs in partition order
+    DevBuf<uint32_t> sort_tile_count, sort_part_count, sort_part_offs;
+    int segments_override = 0;                                  // development knob (ACCMSM_SEGMENTS): point segments of a large host-scalar MSM (1 = no pipelining)
+    int seg0_pct = 12;                                          // share of the first of two segments (ACCMSM_SEG0_PCT)
+    int sort_lb_override = 0;                                   // development knob (ACCMSM_SORT_LB), 0 = automatic; -1 = first-version sort
     DevBuf<affine_t> oneshot_xy, pair_pts[2];   // pair_pts / pair_off: ping-pong lists of the batch-affine rounds
     DevBuf<uint32_t> pair_off[2];
     DevBuf<uint8_t> pair_pref, pair_kinds, pair_tfac, pair_ctot, pair_cfac;
@@ -265,7 +271,7 @@ struct MsmJobs {
     explicit MsmJobs(size_t off) { offset[0] = off; }
 };
 
-MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n) {
+MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, size_t n_for_c) {
     MsmShape sh;
     sh.n = (uint32_t)n;
     sh.njobs = jobs.njobs;
@@ -280,7 +286,7 @@ MsmShape make_shape(const accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, 
         sh.hist_stride = 0;
         sh.ent_stride = (uint32_t)B.n;
     } else {
-        sh.c = pick_window_bits(ctx, n);
+        sh.c = pick_window_bits(ctx, n_for_c);
         sh.nwin = (256 + sh.c - 1) / sh.c;
         sh.nb = 1u << (sh.c - 1);
         sh.sets_per_job = sh.nwin;
@@ -298,78 +304,110 @@ int affine_rounds(const accmsm_ctx *ctx, const MsmShape &sh, size_t n_entries) {
 }
 
 // exclusive scan of counts[0..nkeys) into offsets[0..nkeys] (+ optional copy into cursor)
-int launch_scan(accmsm_ctx *ctx, const uint32_t *counts, uint32_t nkeys, uint32_t *offsets, uint32_t *cursor, cudaStream_t st) {
+int launch_scan(accmsm_ctx *ctx, const uint32_t *counts, uint32_t nkeys, uint32_t *offsets, uint32_t *cursor, cudaStream_t st,
+                SortGate gate = SortGate{nullptr, 0}) {
     uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
     if (ntiles <= SCAN_ONE_CTA_TILES) {
-        k_scan<<<1, 1024, 0, st>>>(counts, nkeys, offsets, cursor);
+        k_scan<<<1, 1024, 0, st>>>(counts, nkeys, offsets, cursor, gate);
         ctx->launches++;
     } else {
         CU(ctx, ctx->tile_sums.ensure(ntiles));
         CU(ctx, ctx->tile_offs.ensure(ntiles + 1));
-        k_scan_tile_sums<<<ntiles, 1024, 0, st>>>(counts, nkeys, ctx->tile_sums.p);
-        k_scan<<<1, 1024, 0, st>>>(ctx->tile_sums.p, ntiles, ctx->tile_offs.p, nullptr);
-        k_scan_tiles<<<ntiles, 1024, 0, st>>>(counts, nkeys, ctx->tile_offs.p, offsets, cursor);
+        k_scan_tile_sums<<<ntiles, 1024, 0, st>>>(counts, nkeys, ctx->tile_sums.p, gate);
+        k_scan<<<1, 1024, 0, st>>>(ctx->tile_sums.p, ntiles, ctx->tile_offs.p, nullptr, gate);
+        k_scan_tiles<<<ntiles, 1024, 0, st>>>(counts, nkeys, ctx->tile_offs.p, offsets, cursor, gate);
         ctx->launches += 3;
     }
     return ACCMSM_OK;
 }
 
-// The MSM pipeline after the digits kernel has been chosen.  Leaves the per-window sums combined into
-// either a device partial (d_partial) or the normalised affine result in ctx->d_out_affine/d_out_inf.
-// A host upload that is consumed chunk by chunk: feed(c) enqueues the copy of scalars [c * chunk_elems, ...) on the copy
-// stream and records events[c]; run_msm launches the digit kernel of chunk c behind that event, so the digit
-// decomposition of a chunk overlaps the PCIe transfer of the following ones.
-struct DigitChunks {
-    uint32_t nchunks = 0, chunk_elems = 0;
-    std::function<int(uint32_t)> feed;
-    const cudaEvent_t *events = nullptr;
-};
+constexpr size_t SORT_SMEM_OPT_IN = 220 * 1024;      // dynamic shared memory the sort kernels may use (227 KB per CTA minus their static part)
+template <class Src> bool sort_opt_in() {
+    return cudaFuncSetAttribute(k_sort_tiles<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_OPT_IN) == cudaSuccess;
+}
 
+// ---- the MSM pipeline in two stages ---------------------------------------------------------------------------------
+// msm_accumulate: sort the (bucket, point) pairs of `n` (base, scalar) pairs and accumulate them into ctx->buckets.
+//                 into = false: every non-empty bucket is overwritten (empty ones are never read: the reduction tests
+//                 the offsets); into = true: the sums are ADDED to zero-initialised buckets -- several point segments of
+//                 one MSM then share the bucket set (msm_host_scalars pipelines their uploads).
+// msm_reduce:     bucket reduction, (plain key: Horner over windows), extra partials, normalisation / raw partial.
+// n_for_c: the length that picks the window size of a plain key (all segments of one MSM must agree on it).
 template <int CURVE, class Src>
-int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const Src &src,
-            const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
-            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr, const DigitChunks *chunks = nullptr) {
-    if (!d_out_aff) { d_out_aff = ctx->d_out_affine; d_out_inf = ctx->d_out_inf; }
-    MsmShape sh = make_shape(ctx, B, jobs, n);
+int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, size_t n_for_c, const Src &src, bool into,
+                   cudaStream_t st, MsmShape *sh_out) {
+    MsmShape sh = make_shape(ctx, B, jobs, n, n_for_c);
+    *sh_out = sh;
     const bool tabled = sh.ent_stride != 0;
-    const uint32_t nsets = sh.njobs * sh.sets_per_job;          // bucket sets to reduce
     const affine_t *points = tabled ? B.d_table : B.d_xy;
     const size_t n_entries = (size_t)sh.n * sh.nwin * sh.njobs;
     if (n_entries >= (size_t(1) << 31)) return fail_arg(ctx, "msm: jobs * windows * n must be < 2^31");
-    CU(ctx, ctx->digits.ensure(n_entries));
     CU(ctx, ctx->entries.ensure(n_entries));
-    CU(ctx, ctx->hist.ensure(sh.nkeys));
+    CU(ctx, ctx->hist.ensure(sh.nkeys));          // also scratch of the batch-affine rounds
     CU(ctx, ctx->offsets.ensure(sh.nkeys + 1));
-    CU(ctx, ctx->cursor.ensure(sh.nkeys));
     CU(ctx, ctx->buckets.ensure(sh.nkeys));
     { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
 
-    mark(ctx, ST_DIGITS, st);
-    CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), st));
-    if (chunks) {
-        for (uint32_t c = 0; c < chunks->nchunks; c++) {
-            const uint32_t i0 = c * chunks->chunk_elems, i1 = std::min<uint32_t>(sh.n, i0 + chunks->chunk_elems);
-            { int frc = chunks->feed(c); if (frc) return frc; }
-            CU(ctx, cudaStreamWaitEvent(st, chunks->events[c], 0));
-            dim3 blocks((i1 - i0 + 255) / 256, sh.njobs);
-            k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p, i0, i1);
-            ctx->launches++;
-        }
-    } else {
-        dim3 blocks((sh.n + 255) / 256, sh.njobs);
-        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p, 0u, sh.n);
-        ctx->launches++;
+    // Sort of the (bucket key, table index | sign) pairs.  Long passes: two-level radix sort staged through shared memory
+    // (sort.cuh: digits never touch HBM, no global atomics), with the first-version counting sort gated behind it for skewed
+    // inputs.  Short passes: the counting sort alone (3 launches; with a few thousand pairs nothing is bandwidth-bound).
+    const bool radix = ctx->sort_lb_override >= 0 && n_entries >= (size_t(1) << 17) && sh.nkeys >= 1024u;
+    SortGate fallback{nullptr, 0};
+    if (radix) {
+        SortPlan pl;
+        pl.lb = ctx->sort_lb_override > 0 ? (uint32_t)ctx->sort_lb_override : 9;      // measured: 9 beats 10 and 11 at 2^19 buckets
+        pl.lb = std::min(SORT_MAX_LB, std::max(9u, pl.lb));
+        while (((sh.nkeys + (1u << pl.lb) - 1) >> pl.lb) > SORT_MAX_PARTS && pl.lb < SORT_MAX_LB) pl.lb++;
+        pl.nparts = (sh.nkeys + (1u << pl.lb) - 1) >> pl.lb;
+        if (pl.nparts > SORT_MAX_PARTS) return fail_arg(ctx, "msm: too many bucket sets in one pass");
+        pl.tiles_per_job = (sh.n + SORT_TILE - 1) / SORT_TILE;
+        pl.ntiles = pl.tiles_per_job * sh.njobs;
+        // shared-memory staging: a tile's pairs (write pass), a partition's entries (bucket pass, 1.25 x the mean size)
+        pl.stage_pairs = (uint32_t)SORT_TILE * sh.nwin <= SORT_STAGE_MAX ? (uint32_t)SORT_TILE * sh.nwin : 0u;
+        pl.bucket_cap = (uint32_t)std::min<size_t>(49152, std::max<size_t>(4096, n_entries / pl.nparts * 5 / 4 + 1024));
+        CU(ctx, ctx->sort_tile_count.ensure((size_t)2 * pl.ntiles * pl.nparts));
+        CU(ctx, ctx->sort_part_count.ensure(pl.nparts + 1));
+        CU(ctx, ctx->sort_part_offs.ensure(pl.nparts + 1));
+        CU(ctx, ctx->sort_pairs.ensure(n_entries));
+        uint32_t *tile_count = ctx->sort_tile_count.p, *tile_hist = tile_count + (size_t)pl.ntiles * pl.nparts;
+        uint32_t *max_part = ctx->sort_part_count.p + pl.nparts;
+        // skew: one partition holds more than 4 x its share (and more than a CTA streams in ~50 us)
+        const SortGate gate{max_part, (uint32_t)std::min<size_t>(0x7fffffffu, std::max<size_t>(65536, 4 * n_entries / pl.nparts))};
+        fallback = gate;
+        const size_t smem0 = (size_t)2 * pl.nparts * sizeof(uint32_t);
+        const size_t smem1 = smem0 + (size_t)pl.stage_pairs * sizeof(uint2);
+        const size_t smem2 = ((size_t(1) << pl.lb) + pl.bucket_cap) * sizeof(uint32_t);
+        if (smem1 > SORT_SMEM_OPT_IN || smem2 > SORT_SMEM_OPT_IN) return fail_arg(ctx, "msm: sort staging exceeds shared memory");
+        mark(ctx, ST_DIGITS, st);
+        CU(ctx, cudaMemsetAsync(max_part, 0, sizeof(uint32_t), st));
+        k_sort_tiles<Src, false><<<pl.ntiles, SORT_THREADS, smem0, st>>>(src, sh, B.d_inf, pl, 0u, pl.tiles_per_job, tile_count, tile_hist, nullptr, nullptr, gate);
+        mark(ctx, ST_SCAN, st);
+        k_sort_tile_scan<<<(pl.nparts + TS_PARTS - 1) / TS_PARTS, TS_PARTS * TS_SEGS, 0, st>>>(tile_count, pl.ntiles, pl.nparts, ctx->sort_part_count.p, max_part);
+        ctx->launches += 2;
+        { int src2 = launch_scan(ctx, ctx->sort_part_count.p, pl.nparts, ctx->sort_part_offs.p, nullptr, st); if (src2) return src2; }
+        mark(ctx, ST_SCATTER, st);
+        k_sort_tiles<Src, true><<<pl.ntiles, SORT_THREADS, smem1, st>>>(src, sh, B.d_inf, pl, 0u, pl.tiles_per_job, tile_count, tile_hist, ctx->sort_part_offs.p, ctx->sort_pairs.p, gate);
+        k_sort_buckets<<<pl.nparts, SORT_BUCKET_THREADS, smem2, st>>>(ctx->sort_pairs.p, ctx->sort_part_offs.p, pl.lb, sh.nkeys, pl.bucket_cap, ctx->offsets.p, ctx->entries.p, gate);
+        ctx->launches += 2;
     }
-    mark(ctx, ST_SCAN, st);
-    { int src = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p, st); if (src) return src; }
-    mark(ctx, ST_SCATTER, st);
     {
-        dim3 blocks((sh.n + 255) / 256, sh.njobs);
-        k_scatter<<<blocks, 256, 0, st>>>(sh, ctx->digits.p, ctx->cursor.p, ctx->entries.p);
-        ctx->launches++;
+        // first-version counting sort: the only sort of a short pass; behind the gate of a long one (its kernels return at
+        // once unless the radix sort stood down)
+        CU(ctx, ctx->digits.ensure(n_entries));
+        CU(ctx, ctx->cursor.ensure(sh.nkeys));
+        if (!radix) mark(ctx, ST_DIGITS, st);
+        CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), st));
+        // behind the gate: a small grid (grid-stride loops), so standing down costs next to nothing
+        dim3 blocks(radix ? std::min<uint32_t>((sh.n + 255) / 256, (uint32_t)ctx->sm_count * 8) : (sh.n + 255) / 256, sh.njobs);
+        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p, 0u, sh.n, fallback);
+        if (!radix) mark(ctx, ST_SCAN, st);
+        { int src2 = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p, st, fallback); if (src2) return src2; }
+        if (!radix) mark(ctx, ST_SCATTER, st);
+        k_scatter<<<blocks, 256, 0, st>>>(sh, ctx->digits.p, ctx->cursor.p, ctx->entries.p, fallback);
+        ctx->launches += 2;
     }
     mark(ctx, ST_ACCUMULATE, st);
-    if (sh.nkeys <= ACC_WARP_MAX_KEYS && n_entries <= ACC_WARP_MAX_ENTRIES) {
+    if (!into && sh.nkeys <= ACC_WARP_MAX_KEYS && n_entries <= ACC_WARP_MAX_ENTRIES) {
         // short MSM: one group of four replica warps per bucket, no slice merging (k_accumulate_warp_coop in msm.cuh)
         k_accumulate_warp_coop<CURVE><<<sh.nkeys, 128, 0, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p, points, ctx->buckets.p);
         ctx->launches++;
@@ -381,14 +419,14 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
         const uint32_t *acc_offsets = ctx->offsets.p, *acc_entries = ctx->entries.p;
         const affine_t *acc_points = points;
         size_t acc_bound = n_entries;
-        int rounds = affine_rounds(ctx, sh, n_entries);
+        int rounds = into ? 0 : affine_rounds(ctx, sh, n_entries);
         for (int r = 0; r < rounds; r++) {
             const size_t out_bound = (acc_bound + sh.nkeys) / 2 + 1;
             CU(ctx, ctx->pair_off[r & 1].ensure(sh.nkeys + 1));
             CU(ctx, ctx->pair_pts[r & 1].ensure(out_bound));
             k_pair_counts<<<(sh.nkeys + 255) / 256, 256, 0, st>>>(acc_offsets, sh.nkeys, ctx->hist.p);
             ctx->launches++;
-            { int src = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->pair_off[r & 1].p, nullptr, st); if (src) return src; }
+            { int src2 = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->pair_off[r & 1].p, nullptr, st); if (src2) return src2; }
             uint32_t pgrid = (uint32_t)((out_bound + (size_t)PAIR_THREADS * PAIR_B - 1) / ((size_t)PAIR_THREADS * PAIR_B));
             CU(ctx, ctx->pair_pref.ensure(out_bound * 32));
             CU(ctx, ctx->pair_kinds.ensure(out_bound));
@@ -416,15 +454,27 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
         CU(ctx, ctx->cta_ids.ensure(2 * grid));
         CU(ctx, ctx->cta_parts.ensure(2 * grid));
         size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
-        k_accumulate<CURVE><<<grid, ACC_THREADS, smem, st>>>(acc_offsets, sh.nkeys, acc_entries,
-                                                              acc_points, ctx->buckets.p,
-                                                              ctx->cta_ids.p, ctx->cta_parts.p);
+        if (into) k_accumulate<CURVE, true><<<grid, ACC_THREADS, smem, st>>>(acc_offsets, sh.nkeys, acc_entries, acc_points, ctx->buckets.p,
+                                                                              ctx->cta_ids.p, ctx->cta_parts.p);
+        else k_accumulate<CURVE, false><<<grid, ACC_THREADS, smem, st>>>(acc_offsets, sh.nkeys, acc_entries, acc_points, ctx->buckets.p,
+                                                                          ctx->cta_ids.p, ctx->cta_parts.p);
         mark(ctx, ST_FIXUP, st);
         uint32_t ns = 2 * grid;
         size_t smem2 = ns * (sizeof(xyzz_t) + sizeof(uint32_t));
         k_fixup<CURVE><<<1, FIX_THREADS, smem2, st>>>(ctx->cta_ids.p, ctx->cta_parts.p, ns, ctx->buckets.p);
         ctx->launches += 2;
     }
+    return ACCMSM_OK;
+}
+
+// use_offsets = false: every bucket holds a valid (possibly identity) point and the emptiness test on the offsets of the
+// last accumulated segment must not be used
+template <int CURVE>
+int msm_reduce(accmsm_ctx *ctx, const MsmShape &sh, bool use_offsets, const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial,
+               bool normalise, cudaStream_t st, affine_t *d_out_aff, uint32_t *d_out_inf) {
+    if (!d_out_aff) { d_out_aff = ctx->d_out_affine; d_out_inf = ctx->d_out_inf; }
+    const uint32_t nsets = sh.njobs * sh.sets_per_job;          // bucket sets to reduce
+    const uint32_t *offs = use_offsets ? ctx->offsets.p : nullptr;
     mark(ctx, ST_REDUCE, st);
     const xyzz_t *window_sums = nullptr;
     {
@@ -446,9 +496,9 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
             // first level: cooperative groups while the grid is small enough to be latency-bound (measured: 0.132 vs 0.147 ms
             // with 256 outputs, 0.202 vs 0.175 ms with 512), plain warps when it is throughput-bound (2^19 buckets)
             if ((R0 + C0) * nsets <= 320u)
-                k_sums_coop<CURVE><<<dim3(R0 + C0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, scratch, R0 + C0, t0);
+                k_sums_coop<CURVE><<<dim3(R0 + C0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, offs, scratch, R0 + C0, t0);
             else
-                k_sums<CURVE, RED_L0_BLK><<<dim3(R0 + C0, nsets), RED_L0_BLK, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, scratch, R0 + C0, t0);
+                k_sums<CURVE, RED_L0_BLK><<<dim3(R0 + C0, nsets), RED_L0_BLK, 0, st>>>(ctx->buckets.p, N0, offs, scratch, R0 + C0, t0);
             t1.ntasks = 4;
             t1.t[0] = SumTask{0, 0, R0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, R0 / 32, 1, 32};
             t1.t[2] = SumTask{R0, 64, C0 / 32, 32, 32, 1};   t1.t[3] = SumTask{R0, 96, 32, C0 / 32, 1, 32};
@@ -458,13 +508,13 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
         } else if (N0 > 32) {
             t1.ntasks = 2;
             t1.t[0] = SumTask{0, 0, N0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, N0 / 32, 1, 32};
-            k_sums_coop<CURVE><<<dim3(N0 / 32 + 32, nsets), 128, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
+            k_sums_coop<CURVE><<<dim3(N0 / 32 + 32, nsets), 128, 0, st>>>(ctx->buckets.p, N0, offs, leaf, 128, t1);
             ctx->launches++;
             nlevels = 1;
         } else {
             t1.ntasks = 1;
             t1.t[0] = SumTask{0, 0, N0, 1, 1, 1};
-            k_sums_coop<CURVE><<<dim3(N0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, ctx->offsets.p, leaf, 128, t1);
+            k_sums_coop<CURVE><<<dim3(N0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, offs, leaf, 128, t1);
             ctx->launches++;
             nlevels = 0;
         }
@@ -485,23 +535,34 @@ int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, cons
     return ws_release(ctx, st);
 }
 
+// The whole pipeline over one segment.  Leaves the per-window sums combined into either a device partial (d_partial) or the
+// normalised affine result in ctx->d_out_affine / d_out_inf (or d_out_aff / d_out_inf).
+template <int CURVE, class Src>
+int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const Src &src,
+            const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
+            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
+    MsmShape sh;
+    int rc = msm_accumulate<CURVE>(ctx, B, jobs, n, n, src, false, st, &sh);
+    if (rc) return rc;
+    return msm_reduce<CURVE>(ctx, sh, true, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+}
+
 // run_msm over scalar vectors resident in HBM (one pointer per job), dispatched on the key's curve
 int msm_mem(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const uint8_t *const *d_scalars, int mont,
             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
-            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr, const DigitChunks *chunks = nullptr) {
+            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
     if (B.curve == 0) {
         MemScalars<1> src; src.montgomery = mont;
         for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
-        return run_msm<0>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf, chunks);
+        return run_msm<0>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
     }
     MemScalars<0> src; src.montgomery = mont;
     for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
-    return run_msm<1>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf, chunks);
+    return run_msm<1>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
 }
 int msm_mem1(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint8_t *d_scalars, int mont,
-             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
-             const DigitChunks *chunks = nullptr) {
-    return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr, chunks);
+             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st) {
+    return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr);
 }
 
 // Host -> device copy of a scalar / vector buffer.  Page-locked sources go straight to the DMA engine.  Pageable ones
@@ -622,66 +683,97 @@ const Bases *find_bases(accmsm_ctx *ctx, uint64_t handle) {
 // MSM of host scalars, one vector: uploads and enqueues on the ctx stream.  d_extra/n_extra: XYZZ partials added before
 // normalisation.  d_partial (nullable): where the un-normalised sum goes (DEVICE memory, possibly a peer GPU's);
 // normalise: the affine image goes to ctx->d_out_affine.  The caller fetches / synchronises.
+//
+// Large vectors (>= 16 MiB) hide the PCIe transfer behind the arithmetic: the points are cut into two segments of about
+// 1/8 and 7/8 of the vector (measured best of 12 / 25 / 37 %: profiles/r02i_*; the accumulation of a segment takes ~4x as long as the upload of the same number of
+// scalars), the upload runs on a copy stream in 4 MiB chunks, and the second segment travels while the first one is sorted
+// and accumulated; both segments add into ONE zero-initialised bucket set (k_accumulate `into` mode: no extra
+// additions), then one reduction.  Exposed transfer: the first fifth.  Pageable sources are staged chunk by chunk into
+// page-locked memory by 4 threads on the way.
 int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint64_t *scalars, int mont,
                      const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise) {
     cudaStream_t st = ctx->stream;
-    clear_marks(ctx);
     CU(ctx, ctx->scalars.ensure(n * 32));
     mark(ctx, ST_H2D, st);
     constexpr size_t CHUNK = 4u << 20;
     const size_t bytes = n * 32;
-    if (bytes >= 4 * CHUNK) {
-        // large vectors: the upload runs on its own stream in 4 MiB chunks and the digit kernel follows it chunk by chunk,
-        // so only the first chunk's transfer is exposed (the 'digits' stage time then contains the rest of the transfer)
-        if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        DigitChunks ch;
-        ch.nchunks = (uint32_t)((bytes + CHUNK - 1) / CHUNK);
-        ch.chunk_elems = (uint32_t)(CHUNK / 32);
-        while (ctx->chunk_events.size() < ch.nchunks) {
-            cudaEvent_t ev;
-            CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            ctx->chunk_events.push_back(ev);
-        }
-        ch.events = ctx->chunk_events.data();
-        cudaPointerAttributes attr;
-        cudaError_t pe = cudaPointerGetAttributes(&attr, scalars);
-        bool pageable = pe != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
-        if (pe != cudaSuccess) (void)cudaGetLastError();
-        if (pageable) {
-            if (ctx->stage_busy) { CU(ctx, cudaEventSynchronize(ctx->stage_done)); ctx->stage_busy = false; }
-            if (ctx->stage_cap < bytes) {
-                if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-                ctx->h_stage = nullptr; ctx->stage_cap = 0;
-                CU(ctx, cudaMallocHost(&ctx->h_stage, bytes + bytes / 8));
-                ctx->stage_cap = bytes + bytes / 8;
-            }
-        }
-        const char *src = (const char *)scalars;
-        char *stage = (char *)ctx->h_stage;
-        uint8_t *dst = ctx->scalars.p;
-        cudaStream_t cs = ctx->copy_stream;
-        ch.feed = [=](uint32_t c) -> int {
-            const size_t off = (size_t)c * CHUNK, len = std::min(CHUNK, bytes - off);
-            const char *from = src + off;
-            if (pageable) {
-                const int parts = 4;
-#pragma omp parallel for num_threads(parts) schedule(static)
-                for (int p = 0; p < parts; p++) {
-                    size_t lo = len * p / parts, hi = len * (p + 1) / parts;
-                    memcpy(stage + off + lo, src + off + lo, hi - lo);
-                }
-                from = stage + off;
-            }
-            if (cudaMemcpyAsync(dst + off, from, len, cudaMemcpyHostToDevice, cs) != cudaSuccess) return ACCMSM_E_CUDA;
-            if (cudaEventRecord(ch.events[c], cs) != cudaSuccess) return ACCMSM_E_CUDA;
-            return ACCMSM_OK;
-        };
-        int rc = msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, d_partial, normalise, st, &ch);
-        if (rc) { ctx->last_error = "msm: chunked upload failed"; return rc; }
-        return ACCMSM_OK;
+    if (bytes < 4 * CHUNK || ctx->segments_override == 1) {
+        { int urc = upload(ctx, ctx->scalars.p, scalars, bytes, st); if (urc) return urc; }
+        return msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, d_partial, normalise, st);
     }
-    { int urc = upload(ctx, ctx->scalars.p, scalars, bytes, st); if (urc) return urc; }
-    return msm_mem1(ctx, B, offset, n, ctx->scalars.p, mont, d_extra, n_extra, d_partial, normalise, st);
+    if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    const uint32_t nchunks = (uint32_t)((bytes + CHUNK - 1) / CHUNK), chunk_elems = (uint32_t)(CHUNK / 32);
+    while (ctx->chunk_events.size() < nchunks) {
+        cudaEvent_t ev;
+        CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(ev);
+    }
+    cudaPointerAttributes attr;
+    cudaError_t pe = cudaPointerGetAttributes(&attr, scalars);
+    const bool pageable = pe != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+    if (pe != cudaSuccess) (void)cudaGetLastError();
+    if (pageable) {
+        if (ctx->stage_busy) { CU(ctx, cudaEventSynchronize(ctx->stage_done)); ctx->stage_busy = false; }
+        if (ctx->stage_cap < bytes) {
+            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+            ctx->h_stage = nullptr; ctx->stage_cap = 0;
+            CU(ctx, cudaMallocHost(&ctx->h_stage, bytes + bytes / 8));
+            ctx->stage_cap = bytes + bytes / 8;
+        }
+    }
+    const char *src = (const char *)scalars;
+    char *stage = (char *)ctx->h_stage;
+    // the copy stream must not overwrite scalars an earlier call on this ctx is still reading
+    { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
+    CU(ctx, cudaEventRecord(ctx->stage_done, st));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_done, 0));
+    auto feed = [&](uint32_t c) -> int {
+        const size_t off = (size_t)c * CHUNK, len = std::min(CHUNK, bytes - off);
+        const char *from = src + off;
+        if (pageable) {
+            const int parts = 4;
+#pragma omp parallel for num_threads(parts) schedule(static)
+            for (int p = 0; p < parts; p++) {
+                size_t lo = len * p / parts, hi = len * (p + 1) / parts;
+                memcpy(stage + off + lo, src + off + lo, hi - lo);
+            }
+            from = stage + off;
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->scalars.p + off, from, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
+        return ACCMSM_OK;
+    };
+    // segment boundaries on chunk boundaries
+    const int nseg = ctx->segments_override > 1 ? ctx->segments_override : 2;
+    std::vector<uint32_t> seg_end;       // in chunks
+    if (nseg == 2) { seg_end.push_back(std::max(1u, (nchunks * (uint32_t)ctx->seg0_pct + 50) / 100)); seg_end.push_back(nchunks); }
+    else for (int g = 1; g <= nseg; g++) seg_end.push_back(std::max<uint32_t>(g, (uint32_t)((uint64_t)nchunks * g / nseg)));
+    seg_end.back() = nchunks;
+    MsmShape sh;
+    {   // all segments add into one bucket set: zero = identity
+        const MsmShape s0 = make_shape(ctx, B, MsmJobs(offset), n, n);
+        CU(ctx, ctx->buckets.ensure(s0.nkeys));
+        CU(ctx, cudaMemsetAsync(ctx->buckets.p, 0, (size_t)s0.nkeys * sizeof(xyzz_t), st));
+    }
+    uint32_t c0 = 0;
+    for (size_t g = 0; g < seg_end.size(); g++) {
+        const uint32_t c1 = std::min(seg_end[g], nchunks);
+        if (c1 <= c0) continue;
+        for (uint32_t c = c0; c < c1; c++) { int frc = feed(c); if (frc) return frc; }
+        CU(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[c1 - 1], 0));
+        const size_t e0 = (size_t)c0 * chunk_elems, e1 = std::min<size_t>(n, (size_t)c1 * chunk_elems);
+        const uint8_t *ptr = ctx->scalars.p + e0 * 32;
+        int rc;
+        if (B.curve == 0) { MemScalars<1> ms; ms.montgomery = mont; for (uint32_t j = 0; j < MAX_JOBS; j++) ms.ptr[j] = j ? nullptr : ptr;
+                            rc = msm_accumulate<0>(ctx, B, MsmJobs(offset + e0), e1 - e0, n, ms, true, st, &sh); }
+        else { MemScalars<0> ms; ms.montgomery = mont; for (uint32_t j = 0; j < MAX_JOBS; j++) ms.ptr[j] = j ? nullptr : ptr;
+               rc = msm_accumulate<1>(ctx, B, MsmJobs(offset + e0), e1 - e0, n, ms, true, st, &sh); }
+        if (rc) return rc;
+        c0 = c1;
+    }
+    if (pageable) { CU(ctx, cudaEventRecord(ctx->stage_done, ctx->copy_stream)); ctx->stage_busy = true; }
+    if (B.curve == 0) return msm_reduce<0>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr);
+    return msm_reduce<1>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr);
 }
 
 // identity partial(s) into d_out[0..k)
@@ -793,6 +885,9 @@ int accmsm_init(accmsm_ctx **out, int device) {
     accmsm_ctx *ctx = new accmsm_ctx();
     ctx->device = device;
     if (const char *e = getenv("ACCMSM_AFFINE_ROUNDS")) ctx->affine_rounds_override = atoi(e);
+    if (const char *e = getenv("ACCMSM_SORT_LB")) ctx->sort_lb_override = atoi(e);
+    if (const char *e = getenv("ACCMSM_SEGMENTS")) ctx->segments_override = atoi(e);
+    if (const char *e = getenv("ACCMSM_SEG0_PCT")) ctx->seg0_pct = std::min(90, std::max(1, atoi(e)));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
@@ -807,13 +902,25 @@ int accmsm_init(accmsm_ctx **out, int device) {
     // shared-memory opt-in and resident CTAs per SM for the accumulate kernels
     size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
     size_t smem_fix = (size_t)FIX_THREADS * FIX_PER_T * (sizeof(xyzz_t) + sizeof(uint32_t));
-    ok = ok && cudaFuncSetAttribute(k_accumulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_accumulate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_accumulate<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_accumulate<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_accumulate<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_accumulate<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+    // the sort kernels opt in ONCE to the most dynamic shared memory they can ever ask for: the attribute is per function
+    // and device, not per ctx, and the ctxs of a device group launch concurrently from several threads
+    ok = ok && sort_opt_in<MemScalars<0>>() && sort_opt_in<MemScalars<1>>() && sort_opt_in<IpaScalars<0>>() && sort_opt_in<IpaScalars<1>>() &&
+         sort_opt_in<IpaRoundScalars<0>>() && sort_opt_in<IpaRoundScalars<1>>() &&
+         cudaFuncSetAttribute(k_sort_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_OPT_IN) == cudaSuccess;
+    {   // k_tvecs: 2 n_in TVEC_THREADS field elements, n_in <= VEC_MAX_INPUTS
+        const int tv = 2 * VEC_MAX_INPUTS * TVEC_THREADS * (int)sizeof(fe_t);
+        ok = ok && cudaFuncSetAttribute(k_tvecs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tv) == cudaSuccess &&
+             cudaFuncSetAttribute(k_tvecs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tv) == cudaSuccess;
+    }
     ok = ok && cudaFuncSetAttribute(k_fixup<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem_fix, 227 * 1024)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_fixup<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(smem_fix, 227 * 1024)) == cudaSuccess;
     if (ok) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->acc_ctas_per_sm[0], k_accumulate<0>, ACC_THREADS, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->acc_ctas_per_sm[1], k_accumulate<1>, ACC_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->acc_ctas_per_sm[0], k_accumulate<0, false>, ACC_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->acc_ctas_per_sm[1], k_accumulate<1, false>, ACC_THREADS, smem);
         for (int c = 0; c < 2; c++) {
             if (ctx->acc_ctas_per_sm[c] < 1) ctx->acc_ctas_per_sm[c] = 1;
             // k_fixup holds 2 slots per accumulate CTA: at most FIX_THREADS * FIX_PER_T slots
@@ -847,6 +954,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
     ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release();
+    ctx->sort_pairs.release(); ctx->sort_tile_count.release(); ctx->sort_part_count.release(); ctx->sort_part_offs.release();
     for (int i = 0; i < 2; i++) { ctx->pair_pts[i].release(); ctx->pair_off[i].release(); }
     ctx->fold_partial.release(); ctx->fold_flag.release();
     ctx->pair_pref.release(); ctx->pair_kinds.release(); ctx->pair_tfac.release(); ctx->pair_ctot.release(); ctx->pair_cfac.release();

@@ -163,6 +163,15 @@ template <int SFIELD> struct IpaRoundScalars {
     }
 };
 
+// The first-version sort kernels below double as the fallback of the shared-memory radix sort (sort.cuh) for skewed
+// scalar distributions: with a gate they run only when the largest partition the radix sort counted exceeds `thr`
+// (decided on the device, no host round trip); max_part == nullptr: always run.
+struct SortGate {
+    const uint32_t *max_part;
+    uint32_t thr;
+};
+ACC_D bool gate_closed(const SortGate &g) { return g.max_part && *g.max_part <= g.thr; }
+
 // bits [pos, pos + c) of a 256-bit little-endian integer, c <= 24
 ACC_D uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
     uint32_t limb = pos >> 5, off = pos & 31;
@@ -178,15 +187,15 @@ ACC_D uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
 template <class Src>
 __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint8_t *__restrict__ base_is_identity,
                                                  uint32_t *__restrict__ digits, uint32_t *__restrict__ hist,
-                                                 uint32_t i0, uint32_t i1) {
-    // scalars [i0, i1) of every job: the whole vector in one launch, or one chunk of a host upload that is still in flight
-    uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+                                                 uint32_t i0, uint32_t i1, SortGate gate) {
+    if (gate_closed(gate)) return;
+    // scalars [i0, i1) of every job; grid-stride, so a gated launch can use a small grid that costs nothing when it stands down
     const uint32_t job = blockIdx.y;
-    if (i >= i1) return;
-    fe_t s = src.canonical(job, i);
-    if (base_is_identity && base_is_identity[msm_base_index(sh, job, i)]) s = Fp<0>::zero();   // identity bases contribute nothing
     digits += (size_t)job * sh.nwin * sh.n;
     hist += (size_t)job * sh.sets_per_job * sh.nb;
+    for (uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += gridDim.x * blockDim.x) {
+    fe_t s = src.canonical(job, i);
+    if (base_is_identity && base_is_identity[msm_base_index(sh, job, i)]) s = Fp<0>::zero();   // identity bases contribute nothing
     const uint32_t half = 1u << (sh.c - 1);
     const unsigned am = __activemask();            // lanes with i < n (the others have returned)
     const uint32_t lane = threadIdx.x & 31;
@@ -210,6 +219,7 @@ __global__ void __launch_bounds__(256) k_digits(Src src, MsmShape sh, const uint
         const uint32_t key = mag ? w * sh.hist_stride + mag - 1 : NONE_ID;
         const unsigned peers = __match_any_sync(am, key);      // lanes of this warp that hit the same bucket
         if (mag && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+    }
     }
 }
 
@@ -270,27 +280,30 @@ ACC_D uint32_t scan_tile(const uint32_t *__restrict__ hist, uint32_t nkeys, uint
 }
 
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict__ hist, uint32_t nkeys,
-                                                uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor) {
+                                                uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor, SortGate gate) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t total_s;
+    if (gate_closed(gate)) return;
     uint32_t carry = 0;
     for (uint32_t base = 0; base < nkeys; base += SCAN_TILE)
         carry += scan_tile(hist, nkeys, base, carry, offsets, cursor, warp_sums, &total_s);
     if (threadIdx.x == 0) offsets[nkeys] = carry;
 }
 __global__ void __launch_bounds__(1024) k_scan_tile_sums(const uint32_t *__restrict__ hist, uint32_t nkeys,
-                                                          uint32_t *__restrict__ tile_sums) {
+                                                          uint32_t *__restrict__ tile_sums, SortGate gate) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t total_s;
+    if (gate_closed(gate)) return;
     uint32_t total = scan_tile(hist, nkeys, blockIdx.x * SCAN_TILE, 0, nullptr, nullptr, warp_sums, &total_s);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 // tile_offs = exclusive scan of the tile sums (ntiles + 1 entries, the last one is the grand total)
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict__ hist, uint32_t nkeys,
                                                       const uint32_t *__restrict__ tile_offs, uint32_t *__restrict__ offsets,
-                                                      uint32_t *__restrict__ cursor) {
+                                                      uint32_t *__restrict__ cursor, SortGate gate) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t total_s;
+    if (gate_closed(gate)) return;
     scan_tile(hist, nkeys, blockIdx.x * SCAN_TILE, tile_offs[blockIdx.x], offsets, cursor, warp_sums, &total_s);
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) offsets[nkeys] = tile_offs[gridDim.x];
 }
@@ -299,12 +312,12 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict_
 // k_scatter: entries[cursor[key]++] = point index | sign
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__restrict__ digits,
-                                                  uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                  uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries, SortGate gate) {
+    if (gate_closed(gate)) return;
     const uint32_t job = blockIdx.y;
-    if (i >= sh.n) return;
     digits += (size_t)job * sh.nwin * sh.n;
     cursor += (size_t)job * sh.sets_per_job * sh.nb;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sh.n; i += gridDim.x * blockDim.x) {
     const uint32_t base_index = msm_base_index(sh, job, i);
     const unsigned am = __activemask();
     const uint32_t lane = threadIdx.x & 31;
@@ -318,6 +331,7 @@ __global__ void __launch_bounds__(256) k_scatter(MsmShape sh, const uint32_t *__
         if (mag && lane == lead) pos = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
         pos = __shfl_sync(am, pos, lead) + __popc(peers & ((1u << lane) - 1u));
         if (mag) entries[pos] = (w * sh.ent_stride + base_index) | (enc & 0x80000000u);
+    }
     }
 }
 
@@ -386,11 +400,15 @@ ACC_D affine_t affine_identity_marker() {
 // ------------------------------------------------------------------------------------------------
 // k_accumulate
 // ------------------------------------------------------------------------------------------------
-template <int CURVE>
+template <int CURVE, bool INTO>
 __global__ void __launch_bounds__(ACC_THREADS, 2)
 k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_t *__restrict__ entries,
              const affine_t *__restrict__ bases, xyzz_t *__restrict__ buckets,
              uint32_t *__restrict__ cta_ids, xyzz_t *__restrict__ cta_parts) {
+    constexpr bool into = INTO;
+    // INTO: the buckets already hold the sums of earlier point segments of the same MSM (zero-initialised = identity;
+    // msm_host_scalars pipelines the upload of one segment behind the accumulation of the previous one): the run that
+    // STARTS a bucket continues from the stored value, so merging segments costs one 128-byte load per bucket, no additions
     using Cv = Curve<CURVE>;
     extern __shared__ uint4 smem_raw[];
     xyzz_t *slot_pt = reinterpret_cast<xyzz_t *>(smem_raw);
@@ -422,7 +440,7 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
         // in the mixed add; a bucket boundary only costs the (cheap, divergent) flush of the finished run.
         uint32_t k = lo, bend = offsets[k + 1];
         bool first_run = true;
-        xyzz_t acc = Cv::identity();
+        xyzz_t acc = (into && s == offsets[k]) ? load_xyzz(buckets + k) : Cv::identity();
         // entries == nullptr: "direct" list (after batch-affine rounds, below): entry p IS point p of `bases`, no sign,
         // and x = 2^256 - 1 marks the identity
         uint32_t ent = entries ? entries[s] : s;
@@ -442,6 +460,7 @@ k_accumulate(const uint32_t *__restrict__ offsets, uint32_t nkeys, const uint32_
                     }
                     k = blo; bend = offsets[k + 1];
                 }
+                if (into) acc = load_xyzz(buckets + k);      // entry p is the first of bucket k
             }
             const uint32_t cur_sign = ent >> 31;
             affine_t cur = pt;
