@@ -151,6 +151,24 @@ class Context:
                                                               C.c_size_t(n), C.byref(h)), "register_synthetic_bases")
         return Bases(self, curve, int(h.value), n)
 
+    def register_bases_compressed(self, curve: int, data) -> "Bases":
+        """ark-serialize compressed points (n x 33 B, no length prefix) -> registered key, decompressed on the device"""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        if buf.size % 33:
+            raise ValueError("compressed points are 33 bytes each")
+        n = buf.size // 33
+        h = C.c_uint64(0)
+        self._check(self._lib.accmsm_register_bases_compressed(self._h, C.c_int(curve), _p(buf) if n else None, C.c_size_t(n), C.byref(h)),
+                    "register_bases_compressed")
+        return Bases(self, curve, int(h.value), n)
+
+    def serialize_bases(self, bases: "Bases", offset: int = 0, n: Optional[int] = None) -> bytes:
+        n = bases.n - offset if n is None else n
+        out = np.empty(n * 33, dtype=np.uint8)
+        self._check(self._lib.accmsm_serialize_bases(self._h, C.c_uint64(bases.handle), C.c_size_t(offset), C.c_size_t(n), _p(out) if n else None),
+                    "serialize_bases")
+        return out.tobytes()
+
     def download_bases(self, bases: "Bases", offset: int = 0, n: Optional[int] = None):
         n = bases.n - offset if n is None else n
         out = np.empty((n, 8), dtype=np.uint64)

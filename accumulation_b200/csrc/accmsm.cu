@@ -17,6 +17,7 @@
 #include "sort.cuh"
 #include "vec.cuh"
 #include "ipa.cuh"
+#include "wire.cuh"
 
 using namespace accmsm;
 
@@ -835,6 +836,7 @@ int group_destroy(accmsm_ctx *g);
 int group_register_bases(accmsm_ctx *g, int curve, const uint64_t *xy, const uint8_t *infinity, size_t n, uint64_t seed,
                          uint64_t first_index, bool synthetic, uint64_t *handle);
 int group_release_bases(accmsm_ctx *g, uint64_t handle);
+int group_serialize_bases(accmsm_ctx *g, uint64_t handle, size_t offset, size_t n, uint8_t *out);
 int group_precompute(accmsm_ctx *g, uint64_t handle, int window_bits);
 int group_download_bases(accmsm_ctx *g, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out);
 int group_msm_rows(accmsm_ctx *g, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars, int mont,
@@ -1354,4 +1356,5 @@ int accmsm_ipa_final_key_partial_dev(accmsm_ctx *ctx, uint64_t handle, const uin
 #include "vec_api.inc"
 #include "ipa_api.inc"
 #include "fused_api.inc"
+#include "wire_api.inc"
 #include "multi_api.inc"

@@ -471,6 +471,60 @@ template <int FIELD> struct Fp {
         }
         return acc;
     }
+
+    // ---- square roots (Tonelli-Shanks; both fields have two-adicity 32: m - 1 = 2^32 T) --------------------------
+    // Used to decompress ark-serialize points on the device (wire.cuh): y = sqrt(x^3 + 5).
+    static ACC_HD fe_t sqrt_exp() {      // (T - 1) / 2
+        fe_t e = zero();
+        e.l[0] = FIELD == 0 ? 0xcc969876u : 0xc6237590u; e.l[1] = FIELD == 0 ? 0x04a67c8du : 0x04ca546eu;
+        e.l[2] = 0x11234c7eu; e.l[6] = 0x20000000u;
+        return e;
+    }
+    static ACC_HD fe_t root_of_unity() {  // 5^T: a primitive 2^32-th root of unity (5 is a non-residue in both fields), Montgomery
+        fe_t r;
+        if (FIELD == 0) {
+            r.l[0] = 0xbad6dbf0u; r.l[1] = 0xa28db849u; r.l[2] = 0xd3b539dfu; r.l[3] = 0x9083cd03u;
+            r.l[4] = 0x9dc8448eu; r.l[5] = 0xfba6b9cau; r.l[6] = 0x7b89c6dau; r.l[7] = 0x3ec92874u;
+        } else {
+            r.l[0] = 0x8c9942deu; r.l[1] = 0x21807742u; r.l[2] = 0x21b60494u; r.l[3] = 0xcc495789u;
+            r.l[4] = 0xb2efbee2u; r.l[5] = 0xac2e5d27u; r.l[6] = 0x7f2db056u; r.l[7] = 0x0b79fa89u;
+        }
+        return r;
+    }
+    // out = a square root of a (either one); false when a is not a square
+    static ACC_HD bool sqrt(const fe_t &a, fe_t &out) {
+        if (is_zero(a)) { out = zero(); return true; }
+        const fe_t e = sqrt_exp(), o = one();
+        fe_t w = o;
+        for (int i = 221; i >= 0; i--) {
+            w = mul(w, w);
+            if ((e.l[i >> 5] >> (i & 31)) & 1u) w = mul(w, a);
+        }
+        fe_t x = mul(a, w), b = mul(x, w), z = root_of_unity();
+        uint32_t v = 32;
+        while (!eq(b, o)) {
+            uint32_t k = 0;
+            fe_t b2 = b;
+            while (!eq(b2, o) && k < v) { b2 = mul(b2, b2); k++; }
+            if (k == v) return false;
+            fe_t t = z;
+            for (uint32_t j = 0; j + k + 1 < v; j++) t = mul(t, t);
+            z = mul(t, t); b = mul(b, z); x = mul(x, t); v = k;
+        }
+        out = x;
+        return true;
+    }
+    // a < b as canonical integers (inputs canonical, NOT Montgomery images)
+    static ACC_HD bool lt(const fe_t &a, const fe_t &b) {
+        for (int i = 7; i >= 0; i--) { if (a.l[i] != b.l[i]) return a.l[i] < b.l[i]; }
+        return false;
+    }
+    // a canonical 256-bit integer is a valid field element
+    static ACC_HD bool is_canonical(const fe_t &a) {
+        fe_t m;
+        for (int i = 0; i < 8; i++) m.l[i] = mod_limb(i);
+        return lt(a, m);
+    }
 };
 
 // Fp with the product behind a real call.  The latency-bound tail kernels (one or a few warps walking through

@@ -104,6 +104,13 @@ int accmsm_register_synthetic_bases(accmsm_ctx *ctx, int curve, uint64_t seed, u
                                     size_t n, uint64_t *handle);
 int accmsm_download_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, uint64_t *xy_out);
 
+/* ark-serialize 0.2 wire format (derives at src/ipa_pc_as/data_structures.rs:55, src/hp_as/data_structures.rs:13):
+ * a key as `CanonicalSerialize` writes `Vec<GroupAffine<P>>`, minus the 8-byte length prefix: n x 33 B, each the canonical
+ * little-endian x (32 B) + a flag byte (bit 7: y is the larger of (y, -y); bit 6: infinity).  Decompression (one square root
+ * per point) runs on the device.  Any invalid encoding fails the call with ACCMSM_E_ARG (ark: SerializationError::InvalidData). */
+int accmsm_register_bases_compressed(accmsm_ctx *ctx, int curve, const uint8_t *bytes, size_t n, uint64_t *handle);
+int accmsm_serialize_bases(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, uint8_t *out /* n x 33 */);
+
 /* ---- MSM ------------------------------------------------------------------------------------------
  * ark_ec::msm::VariableBaseMSM::multi_scalar_mul(&bases[offset..offset+n], &scalars[..n]) followed by
  * into_affine().  scalars: HOST pointer, n x 4 u64; scalars_montgomery = 1 takes the Fp256 image that

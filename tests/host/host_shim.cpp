@@ -19,6 +19,7 @@ template <int F> static void binop(int op, const uint32_t *a, const uint32_t *b,
             case 6: r = Fp<F>::to_mont(x); break;
             case 7: r = Fp<F>::neg(x); break;
             case 8: r = Fp<F>::inv_gcd(x); break;
+            case 9: { fe_t t; bool ok = Fp<F>::sqrt(x, t); r = ok ? Fp<F>::mul(t, t) : Fp<F>::zero(); if (!ok) r.l[0] = 0xdeadbeefu; break; }   // sqrt(x)^2, or a marker
             default: r = x;
         }
         memcpy(o + 8 * i, r.l, 32);

@@ -47,3 +47,12 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inc", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.replace("the oracle", "").replace("with the oracle", "") or f == "__none__", f
+
+
+def test_rust_ffi_declarations_are_in_sync_with_the_header():
+    """accmsm-sys/src/ffi.rs is generated from include/accmsm.h: every declared symbol, no drift"""
+    import subprocess, sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_sys_bindings.py"), "--check"]).returncode == 0
+    text = open(os.path.join(ROOT, "accmsm-sys", "src", "ffi.rs")).read()
+    for name in header_symbols():
+        assert f"pub fn {name}(" in text, name

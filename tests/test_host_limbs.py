@@ -70,6 +70,23 @@ def test_field_limb_algorithms(shim, field):
     assert (fe_op(shim, field, 8, small) == cref.fe_inv(field, small)).all()
 
 
+@pytest.mark.parametrize("field", [0, 1])
+def test_tonelli_shanks_square_roots(shim, field):
+    """Fp::sqrt (device header, host build): squares have a root whose square is the input; non-squares are reported"""
+    m = [pyref.P_PALLAS_BASE, pyref.Q_PALLAS_SCALAR][field]
+    a = cref.gen_scalars(field, 11, 300, True)
+    sq = cref.fe_mul(field, a, a)
+    assert (fe_op(shim, field, 9, sq) == sq).all()
+    vals = cref.arr_to_ints(cref.from_mont(field, a))
+    got = fe_op(shim, field, 9, a)
+    for v, g, orig in zip(vals, got, a):
+        is_sq = pow(v, (m - 1) // 2, m) == 1
+        assert (g == orig).all() if is_sq else int(g[0]) & 0xffffffff == 0xdeadbeef
+    edge = cref.to_mont(field, cref.ints_to_arr([0, 1, 4, m - 1, 5]))      # -1 is a square (m = 1 mod 4), 5 is not
+    got = fe_op(shim, field, 9, edge)
+    assert (got[:4] == edge[:4]).all() and int(got[4][0]) & 0xffffffff == 0xdeadbeef
+
+
 def ec_sum(lib, curve, pts, neg, mode):
     pts = np.ascontiguousarray(pts, dtype=np.uint64)
     out = np.empty(8, dtype=np.uint64)
