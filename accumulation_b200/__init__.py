@@ -338,6 +338,15 @@ class Context:
         self._check(self._lib.accmsm_ipa_open_fold(self._h, C.c_uint64(session), _p(_u64(xi_mont)), _p(_u64(xi_inv_mont))),
                     "ipa_open_fold")
 
+    def ipa_open_fold_round(self, session: int, xi_mont):
+        """fold with xi (its inverse is computed in the library) and run the next round: -> ((l, inf), (r, inf)) or None when
+        the opening is folded to length 1"""
+        l, r = np.empty(8, dtype=np.uint64), np.empty(8, dtype=np.uint64)
+        li, ri, done = C.c_uint8(0), C.c_uint8(0), C.c_int(0)
+        self._check(self._lib.accmsm_ipa_open_fold_round(self._h, C.c_uint64(session), _p(_u64(xi_mont)), _p(l), C.byref(li), _p(r),
+                                                         C.byref(ri), C.byref(done)), "ipa_open_fold_round")
+        return None if done.value else ((l, int(li.value)), (r, int(ri.value)))
+
     def ipa_open_finish(self, session: int):
         fk, c = np.empty(8, dtype=np.uint64), np.empty(4, dtype=np.uint64)
         self._check(self._lib.accmsm_ipa_open_finish(self._h, C.c_uint64(session), _p(fk), _p(c)), "ipa_open_finish")

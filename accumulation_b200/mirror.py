@@ -103,12 +103,12 @@ class InnerProductArgPC:
         else:
             sess = ctx.ipa_open_begin(ck.bases, cf, k, point, h_prime_xy)
         l_vec, r_vec, challenges, xi = [], [], [], None
-        for _ in range(k):
-            l, r = ctx.ipa_open_round(sess)
+        lr = ctx.ipa_open_round(sess) if k else None
+        while lr is not None:                      # one library call per round: fold (xi^-1 inside) + next round
+            l, r = lr
             xi = np.ascontiguousarray(round_challenge(xi, l, r), dtype=np.uint64).reshape(4)
-            xi_inv = _int_to_fe(field, pow(_fe_to_int(field, xi), -1, _MODULI[field]))
-            ctx.ipa_open_fold(sess, xi, xi_inv)
             l_vec.append(l); r_vec.append(r); challenges.append(xi)
+            lr = ctx.ipa_open_fold_round(sess, xi)
         final_key, c = ctx.ipa_open_finish(sess)
         return l_vec, r_vec, final_key, c, challenges
 

@@ -31,8 +31,36 @@ import numpy as np  # noqa: E402
 
 LOG_N_PER_GPU = 20
 SEED = 0xACC5
-FE_MUL_PEAK_G = 74.9          # measured on this pool's B200 (tools/ubench.cu, profiles/r01_ubench_first.jsonl), Gmul/s
-MULS_PER_MADD = 10            # XYZZ madd-2008-s: 8M + 2S
+MULS_PER_MADD = 10            # XYZZ madd-2008-s: 8M + 2S (one pair of the 8M shares a reduction)
+
+
+def int_peaks():
+    """Integer roofline denominators in the regime k_accumulate runs in: tools/ubench2.cu at 16 warps per SM (128
+    registers), bursts of ~2.5 ms with the effective clock recorded per point (profiles/r02a_ubench2.jsonl).  STATIC: read
+    from the committed profile, not measured in this run."""
+    out = {"fe_mul_gmul_s": None, "fe_mul_eff_mhz": None, "madd_gmul_eq_s": None, "madd_eff_mhz": None, "source": "profiles/r02a_ubench2.jsonl"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02a_ubench2.jsonl")) as f:
+            for line in f:
+                d = json.loads(line)
+                if d.get("warps_per_sm") != 16:
+                    continue
+                if d.get("bench") == "fe_mul":
+                    out["fe_mul_gmul_s"], out["fe_mul_eff_mhz"] = d["g_per_s"], d["eff_mhz"]
+                if d.get("bench") == "madd":
+                    out["madd_gmul_eq_s"], out["madd_eff_mhz"] = d["gmul_equiv_per_s"], d["eff_mhz"]
+    except Exception:
+        pass
+    return out
+
+
+def ncu_static(kernel):
+    """pipe utilisation of the committed `ncu --set full` capture of the shipped build (STATIC, profiles/ncu_static.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_static.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -291,6 +319,7 @@ def main():
     # ---- ipa-pc-as decide tail (metric string: decide ms at degree 2^18, target 2^20), one GPU.  Each degree gets the
     #      key a trimmed CommitterKey of that degree would register: 2^k generators + the hiding generator
     decide = {}
+    extras_cpu = {}
     ipa_keys = {}
     if rank == 0 and world == 1:
         for k in (18, 20):
@@ -311,6 +340,16 @@ def main():
                 ts.append((time.perf_counter() - t0) * 1e3)
                 assert ok
             decide[f"ipa_decide_tail_ms_2^{k}"] = round(statistics.median(ts), 4)
+            if k == 18 and not args.no_cpu_baseline:
+                # CPU restatement of the same tail (compute_coeffs serial like upstream + VariableBaseMSM over windows), same key
+                from oracle import cref
+                kp = ctx.download_bases(ipa_keys[k], 0, 1 << k)
+                t0 = time.perf_counter()
+                okc, cxy, cinf = cref.ipa_check_final_key(0, kp, ch, fk[0], fk[1])
+                dtc = (time.perf_counter() - t0) * 1e3
+                assert okc, "decide tail: GPU final key differs from the oracle"
+                extras_cpu["ipa_decide_tail_ms_2^18"] = {"value": round(dtc, 1), "unit": "ms", "cores": ark_threads(1 << k, cref.num_threads()), "kind": "port",
+                                                         "sample": "whole tail at degree 2^18 (same key and challenges; the GPU key equals the oracle's)"}
 
     # ---- config 4: ipa-pc-as decide at degree 2^20 with the key sharded by point range over all ranks (strong scaling);
     #      every rank expands its own coefficient range of h(X); one all-gather of 128-byte partials
@@ -432,6 +471,67 @@ def main():
             assert ok
             decide[f"ipa_open_ms_2^{k}"] = round(min(ts), 3)
 
+        # ---- AS-shaped prove (examples/scaling-as.rs:91-103: 1 input + 2 copies of an accumulator, zk; src/ipa_pc_as/mod.rs:625-668):
+        #      m = 3 succinct-check group equations (2k + 3 term one-shot MSMs), the combined check polynomial built, evaluated and
+        #      opened on the device (combine + evaluate + open); the sponge stays on the host (Blake2s stand-in)
+        for k in (18,):
+            if k not in ipa_keys:
+                continue
+            n, m_as = 1 << k, 3
+            chm = rand_scalars(m_as * k, SEED + 300).reshape(m_as, k, 4)
+            al = rand_scalars(m_as, SEED + 301)
+            al[:, 2:] = 0                                               # 128-bit linear-combination challenges (src/ipa_pc_as/mod.rs:292-299)
+            rp = rand_scalars(2, SEED + 302)                            # the random linear polynomial of the zk variant
+            zz = rand_scalars(1, SEED + 303).reshape(4)
+            xi0 = rand_scalars(1, SEED + 97).reshape(4)
+            sc_pts = ctx.download_bases(ipa_keys[k], 0, 2 * k + 3)      # stand-ins for C, l_i, r_i, h', final_comm_key of an input
+            sc_scal = rand_scalars(2 * k + 3, SEED + 304)
+            ts = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _j in range(m_as):                                  # succinct_check of every input / accumulator
+                    ctx.msm_oneshot(ab.PALLAS, sc_pts, sc_scal, montgomery=False)
+                sess, ev = ctx.ipa_open_begin_combined(ipa_keys[k], chm, al, zz, None, rp)
+                ctx.ipa_open_use_hiding_generator(sess, n, xi0)
+                xi, lr, nround = None, ctx.ipa_open_round(sess), 0
+                while lr is not None:
+                    xi = squeeze(xi, lr[0], lr[1])
+                    lr = ctx.ipa_open_fold_round(sess, xi)
+                    nround += 1
+                fk, c = ctx.ipa_open_finish(sess)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            assert nround == k
+            decide[f"ipa_as_prove_ms_2^{k}"] = round(min(ts), 3)
+            decide["ipa_as_prove_shape"] = f"m = {m_as} (1 input + 2 accumulator copies), zk, degree 2^{k}: {m_as} succinct-check equations + combine + evaluate + open"
+
+        # ---- CPU restatement of the opening / the AS-shaped prove on a BOUNDED sample (degree 2^12: the CPU folds the key
+        #      generator by generator like upstream, ~4 core-seconds per 2^12 opening), with the GPU's time on the same sample
+        if not args.no_cpu_baseline:
+            from oracle import cref
+            from tests.test_gpu_ipa_open import oracle_open, sponge_stand_in
+            ks = 12
+            pts = cref.gen_points(0, SEED + 400, (1 << ks) + 1)
+            key_s, hp = pts[: 1 << ks], pts[1 << ks]
+            cks = CommitterKey.new(ctx, ab.PALLAS, key_s)
+            cks.bases.precompute()
+            cf = rand_scalars(1 << ks, SEED + 401)
+            zs = rand_scalars(1, SEED + 402).reshape(4)
+            sq = sponge_stand_in(1)
+            InnerProductArgPC.open(cks, cf, zs, hp, sq, log_d=ks)
+            t0 = time.perf_counter()
+            g = InnerProductArgPC.open(cks, cf, zs, hp, sq, log_d=ks)
+            t_gpu = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            e = oracle_open(0, key_s, cf, zs, hp, sq)
+            t_cpu = (time.perf_counter() - t0) * 1e3
+            assert np.array_equal(g[2], e[2]) and np.array_equal(g[3], e[3]) and all(same_pt(a, b) for a, b in zip(g[0] + g[1], e[0] + e[1])), \
+                "IpaPC::open: GPU proof differs from the oracle"
+            extras_cpu["ipa_open_ms_2^12"] = {"value": round(t_cpu, 1), "unit": "ms", "cores": cref.num_threads(), "kind": "port",
+                                              "sample": f"one opening at degree 2^{ks} (bounded sample of the 2^18 workload; proof bit-exact with the GPU's)",
+                                              "gpu_ms_same_sample": round(t_gpu, 3)}
+            cks.bases.release()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -470,7 +570,7 @@ def main():
                    "sharding": f"point-range x{world}, all-gather of one 128 B partial per GPU" if world > 1 else "single GPU",
                    "l2": "flushed (256 MiB memset) between timed steps", "timing": "CUDA events per step on the launching stream"},
         "e2e": {"value": round(e2e, 3), "unit": "Mpts/s", "ms_per_step": round(t_e2e_ms, 4), "h2d_bytes_per_step": count * 32 * world,
-                "d2h_bytes_per_step": 65},
+                "d2h_bytes_per_step": 68},
         "gpu_launches": launches,
         "clocks": clocks,
         "stages_ms": {k: round(v / args.steps, 4) for k, v in stage_acc.items() if v},
@@ -483,10 +583,26 @@ def main():
                            "algorithmic_bytes": 96 * count, "kernel_ms": round(t_acc_ms, 4)}
         madds = count * nwin
         gmul = madds * MULS_PER_MADD / (t_acc_ms * 1e-3) / 1e9
+        ip = int_peaks()
+        ns = ncu_static("k_accumulate")
         out["roofline_int"] = {"kernel": "k_accumulate", "bound": "imad (255-bit Montgomery products)", "achieved": round(gmul, 2),
-                               "peak": FE_MUL_PEAK_G, "unit": "Gmul/s", "frac": round(gmul / FE_MUL_PEAK_G, 4),
-                               "note": "bucket insertions x 10 field products (XYZZ mixed add) / kernel time; peak = measured "
-                                       "fe_mul microbenchmark (tools/ubench.cu), power-capped"}
+                               "peak": ip["fe_mul_gmul_s"], "unit": "Gmul/s", "frac": round(gmul / ip["fe_mul_gmul_s"], 4) if ip["fe_mul_gmul_s"] else None,
+                               "peak_regime": "Fp::mul microbenchmark at the kernel's occupancy (16 warps/SM), ~2.5 ms bursts; the part lowers its clock under "
+                                              "this load (effective MHz recorded)", "peak_eff_mhz": ip["fe_mul_eff_mhz"],
+                               "madd_ceiling": ip["madd_gmul_eq_s"], "frac_of_madd_ceiling": round(gmul / ip["madd_gmul_eq_s"], 4) if ip["madd_gmul_eq_s"] else None,
+                               "madd_ceiling_note": "the kernel's own loop body (XYZZ mixed adds) with operands in registers, no memory traffic",
+                               "insertions": madds, "static_peaks_from": ip["source"],
+                               "ncu_static": ns}
+    t_sort_ms = sum(stage_acc.get(k, 0.0) for k in ("digits", "scan", "scatter")) / args.steps
+    if t_sort_ms > 0 and world == 1:
+        pairs = count * nwin
+        # traffic the two-level sort has to move: scalars read by the count and the write pass, (key, entry) pairs written once
+        # and read by the bucket pass, entries + bucket offsets written
+        sort_bytes = 2 * 32 * count + 2 * 8 * pairs + 4 * pairs + 4 * (1 << (c - 1))
+        out["roofline_sort"] = {"kernels": "k_sort_tiles<count> + k_sort_tile_scan + k_scan + k_sort_tiles<write> + k_sort_buckets", "bound": "hbm",
+                                "achieved": round(sort_bytes / (t_sort_ms * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                                "frac": round(sort_bytes / (t_sort_ms * 1e-3) / 1e9 / hbm_peak, 4), "bytes": sort_bytes, "ms": round(t_sort_ms, 4),
+                                "pairs": pairs}
     if cpu:
         out["cpu_baseline"] = cpu
     if world > 1 and not args.no_verify:
@@ -497,6 +613,8 @@ def main():
     if verified is not None:
         out["verified_vs_oracle"] = verified
     out.update(decide)
+    if extras_cpu:
+        out["cpu_baselines_protocol"] = extras_cpu
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

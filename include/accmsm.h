@@ -216,6 +216,11 @@ int accmsm_ipa_open_use_hiding_generator(accmsm_ctx *ctx, uint64_t session, size
 int accmsm_ipa_open_round(accmsm_ctx *ctx, uint64_t session, uint64_t l_xy[8], uint8_t *l_inf,
                           uint64_t r_xy[8], uint8_t *r_inf);
 int accmsm_ipa_open_fold(accmsm_ctx *ctx, uint64_t session, const uint64_t xi_mont[4], const uint64_t xi_inv_mont[4]);
+/* One call per round of the loop above: fold with the challenge squeezed from the previous (l, r) -- xi^-1 is computed inside,
+ * on the host, like upstream's `round_challenge.inverse()` -- then run the next round; one synchronisation per round.
+ * *done = 1 (l, r untouched) when that fold was the last: accmsm_ipa_open_finish follows. */
+int accmsm_ipa_open_fold_round(accmsm_ctx *ctx, uint64_t session, const uint64_t xi_mont[4], uint64_t l_xy[8], uint8_t *l_inf,
+                               uint64_t r_xy[8], uint8_t *r_inf, int *done);
 int accmsm_ipa_open_finish(accmsm_ctx *ctx, uint64_t session, uint64_t final_key_xy[8], uint64_t c_mont[4]);
 
 /* Multi-GPU opening ("IPA open folding"): the key, the coefficients and the z-vector are sharded
