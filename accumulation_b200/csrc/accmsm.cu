@@ -491,30 +491,46 @@ int msm_reduce(accmsm_ctx *ctx, const MsmShape &sh, bool use_offsets, const xyzz
         SumTasks t1; memset(&t1, 0, sizeof t1);
         if (N0 > 1024) {
             SumTasks t0; memset(&t0, 0, sizeof t0);
-            t0.ntasks = 2;
-            t0.t[0] = SumTask{0, 0, R0, C0, C0, 1};          // R_hi = sum_lo B[hi][lo]
-            t0.t[1] = SumTask{0, R0, C0, R0, 1, C0};         // C_lo = sum_hi B[hi][lo]
+            // R_hi = sum_lo B[hi][lo] (R0 outputs of C0 items), C_lo = sum_hi B[hi][lo] (C0 outputs of R0 items).  With plain
+            // warps the column sums are the longer chains (R0 = 2 C0 for an odd number of index bits: 32 + 5 dependent additions
+            // against 16 + 5): they are cut in two halves of the rows -- outputs interleaved, element 2 lo + h -- so that every warp of
+            // the level has the same depth, and the next level adds the two halves on the fly (SumTask::pair).
+            const bool split = (R0 + C0) * nsets > 320u && R0 > C0;
+            const uint32_t CW = split ? 2 * C0 : C0;          // column-sum array: [2 lo + h] when split
+            CU(ctx, ctx->red_sum[0].ensure((size_t)nsets * (R0 + CW) + 1));
+            scratch = ctx->red_sum[0].p;
+            t0.t[0] = SumTask{0, 0, R0, C0, C0, 1, 1, 0};
+            if (split) {
+                t0.ntasks = 3;
+                t0.t[1] = SumTask{0, R0, C0, R0 / 2, 1, C0, 2, 0};
+                t0.t[2] = SumTask{(R0 / 2) * C0, R0 + 1, C0, R0 / 2, 1, C0, 2, 0};
+            } else {
+                t0.ntasks = 2;
+                t0.t[1] = SumTask{0, R0, C0, R0, 1, C0, 1, 0};
+            }
+            const uint32_t nout0 = R0 + (split ? 2 * C0 : C0);
             // first level: cooperative groups while the grid is small enough to be latency-bound (measured: 0.132 vs 0.147 ms
             // with 256 outputs, 0.202 vs 0.175 ms with 512), plain warps when it is throughput-bound (2^19 buckets)
-            if ((R0 + C0) * nsets <= 320u)
-                k_sums_coop<CURVE><<<dim3(R0 + C0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, offs, scratch, R0 + C0, t0);
+            if (!split && (R0 + C0) * nsets <= 320u)
+                k_sums_coop<CURVE><<<dim3(nout0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, offs, scratch, R0 + CW, t0);
             else
-                k_sums<CURVE, RED_L0_BLK><<<dim3(R0 + C0, nsets), RED_L0_BLK, 0, st>>>(ctx->buckets.p, N0, offs, scratch, R0 + C0, t0);
+                k_sums<CURVE, RED_L0_BLK><<<dim3(nout0, nsets), RED_L0_BLK, 0, st>>>(ctx->buckets.p, N0, offs, scratch, R0 + CW, t0);
             t1.ntasks = 4;
-            t1.t[0] = SumTask{0, 0, R0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, R0 / 32, 1, 32};
-            t1.t[2] = SumTask{R0, 64, C0 / 32, 32, 32, 1};   t1.t[3] = SumTask{R0, 96, 32, C0 / 32, 1, 32};
-            k_sums_coop<CURVE><<<dim3(R0 / 32 + C0 / 32 + 64, nsets), 128, 0, st>>>(scratch, R0 + C0, nullptr, leaf, 128, t1);
+            const uint32_t pw = split ? 2u : 1u, pr = split ? 1u : 0u;
+            t1.t[0] = SumTask{0, 0, R0 / 32, 32, 32, 1, 1, 0};            t1.t[1] = SumTask{0, 32, 32, R0 / 32, 1, 32, 1, 0};
+            t1.t[2] = SumTask{R0, 64, C0 / 32, 32, 32 * pw, pw, 1, pr};   t1.t[3] = SumTask{R0, 96, 32, C0 / 32, pw, 32 * pw, 1, pr};
+            k_sums_coop<CURVE><<<dim3(R0 / 32 + C0 / 32 + 64, nsets), 128, 0, st>>>(scratch, R0 + CW, nullptr, leaf, 128, t1);
             ctx->launches += 2;
             nlevels = 2;
         } else if (N0 > 32) {
             t1.ntasks = 2;
-            t1.t[0] = SumTask{0, 0, N0 / 32, 32, 32, 1};     t1.t[1] = SumTask{0, 32, 32, N0 / 32, 1, 32};
+            t1.t[0] = SumTask{0, 0, N0 / 32, 32, 32, 1, 1, 0};     t1.t[1] = SumTask{0, 32, 32, N0 / 32, 1, 32, 1, 0};
             k_sums_coop<CURVE><<<dim3(N0 / 32 + 32, nsets), 128, 0, st>>>(ctx->buckets.p, N0, offs, leaf, 128, t1);
             ctx->launches++;
             nlevels = 1;
         } else {
             t1.ntasks = 1;
-            t1.t[0] = SumTask{0, 0, N0, 1, 1, 1};
+            t1.t[0] = SumTask{0, 0, N0, 1, 1, 1, 1, 0};
             k_sums_coop<CURVE><<<dim3(N0, nsets), 128, 0, st>>>(ctx->buckets.p, N0, offs, leaf, 128, t1);
             ctx->launches++;
             nlevels = 0;

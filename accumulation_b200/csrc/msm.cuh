@@ -803,6 +803,8 @@ struct SumTask {
     uint32_t len;         // items per output
     uint32_t stride_out;  // input step between consecutive outputs
     uint32_t stride_len;  // input step between consecutive items of one output
+    uint32_t out_stride;  // output step between consecutive outputs (0 = 1)
+    uint32_t pair;        // 1: every item is the sum of two adjacent elements (the two halves of a split column sum)
 };
 struct SumTasks {
     SumTask t[4];
@@ -827,6 +829,7 @@ __global__ void __launch_bounds__(BLK) k_sums(const xyzz_t *__restrict__ in, uin
     for (uint32_t j = threadIdx.x; j < tk.len; j += BLK) {
         uint32_t idx = tk.in_off + o * tk.stride_out + j * tk.stride_len;
         if (!offs || offs[idx + 1] != offs[idx]) { xyzz_t b = load_xyzz(src + idx); Cv::add(acc, b); }
+        if (tk.pair) { xyzz_t b = load_xyzz(src + idx + 1); Cv::add(acc, b); }
     }
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t live = tk.len < BLK ? tk.len : BLK;       // threads that may hold something
@@ -851,7 +854,7 @@ __global__ void __launch_bounds__(BLK) k_sums(const xyzz_t *__restrict__ in, uin
             }
         }
     }
-    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * out_set_stride + tk.out_off + o, acc);
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * out_set_stride + tk.out_off + o * (tk.out_stride ? tk.out_stride : 1u), acc);
 }
 
 // Leaf of the reduction per bucket set: leaf[set][a][j], a < 4, j < 32.  W_a = sum_j j * leaf[a][j] (suffix scan, then a
@@ -917,12 +920,14 @@ __global__ void __launch_bounds__(128) k_sums_coop(const xyzz_t *__restrict__ in
 #pragma unroll 1
     for (uint32_t j0 = 0; j0 < tk.len; j0 += 32) {
         const uint32_t j = j0 + lane;
-        xyzz_t b = Cv::identity();
+        xyzz_t b = Cv::identity(), b2 = Cv::identity();
         if (j < tk.len) {
             uint32_t idx = tk.in_off + o * tk.stride_out + j * tk.stride_len;
             if (!offs || offs[idx + 1] != offs[idx]) b = load_xyzz(src + idx);
+            if (tk.pair) b2 = load_xyzz(src + idx + 1);
         }
         if (j0 == 0) acc = b; else Co::add(c, acc, b);
+        if (tk.pair) Co::add(c, acc, b2);          // uniform across the group
     }
     const uint32_t live = tk.len < 32 ? tk.len : 32;
 #pragma unroll 1
@@ -934,7 +939,7 @@ __global__ void __launch_bounds__(128) k_sums_coop(const xyzz_t *__restrict__ in
             if (lane < (uint32_t)d) acc = t;
         }
     }
-    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * out_set_stride + tk.out_off + o, acc);
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * out_set_stride + tk.out_off + o * (tk.out_stride ? tk.out_stride : 1u), acc);
 }
 
 // The leaf in cooperative form, two launches so that every group is its own CTA (a 16-warp CTA would be capped at 128

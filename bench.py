@@ -217,6 +217,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: accumulation_b200 has no CPU path")
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -568,6 +569,7 @@ def main():
                    "curve": "pallas", "scalars": "uniform 254-bit canonical (BigInteger256)", "window_bits": c, "windows": nwin,
                    "key": "plain (per-window bucket sets)" if args.no_precompute else "precomputed window table 2^(cw)P (built once at registration, one bucket set)",
                    "sharding": f"point-range x{world}, all-gather of one 128 B partial per GPU" if world > 1 else "single GPU",
+                   "host_affinity": numa,
                    "l2": "flushed (256 MiB memset) between timed steps", "timing": "CUDA events per step on the launching stream"},
         "e2e": {"value": round(e2e, 3), "unit": "Mpts/s", "ms_per_step": round(t_e2e_ms, 4), "h2d_bytes_per_step": count * 32 * world,
                 "d2h_bytes_per_step": 68},
@@ -642,6 +644,24 @@ def sharded_open_check(ctx, ab, rank, world, device, k):
         ok = ok and np.array_equal(res[2], efk) and np.array_equal(res[3], ec)
         bases.release()
     return bool(ok)
+
+
+def pin_to_gpu_numa_node(gpu_index):
+    """one process per GPU: run this rank (and first-touch its page-locked scalar buffer) on the CPUs that are local to its
+    GPU's PCIe root, so eight concurrent uploads do not cross the socket interconnect.  Best effort; returns the cpu list."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)"
+    except Exception:
+        pass
+    return None
 
 
 def ark_threads(n, omp_threads):
