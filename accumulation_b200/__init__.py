@@ -238,6 +238,18 @@ class Context:
                                                      C.c_void_p(d_scalars_ptr), C.c_int(int(montgomery)),
                                                      C.c_void_p(d_out_ptr), C.c_void_p(stream)), "msm_partial_dev")
 
+    def msm_partial(self, bases: "Bases", scalars, d_out_ptr: int, montgomery: bool = True, offset: int = 0, n: Optional[int] = None):
+        """one GPU's share of a sharded MSM from HOST scalars (numpy array or raw host pointer): the library uploads (large vectors
+        pipelined behind the accumulation) and leaves the un-normalised partial in device memory at d_out_ptr"""
+        if isinstance(scalars, int):
+            ptr = C.c_void_p(scalars)
+        else:
+            sc = _u64(scalars).reshape(-1, 4)
+            n = sc.shape[0] if n is None else n
+            ptr = _p(sc)
+        self._check(self._lib.accmsm_msm_partial(self._h, C.c_uint64(bases.handle), C.c_size_t(offset), C.c_size_t(n), C.c_size_t(1), ptr,
+                                                 C.c_int(int(montgomery)), C.c_size_t(0), None, C.c_void_p(d_out_ptr)), "msm_partial")
+
     def combine_partials_dev(self, curve: int, d_partials_ptr: int, k: int, stream: int = 0):
         out = np.empty(8, dtype=np.uint64)
         inf = C.c_uint8(0)

@@ -461,6 +461,9 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
                                                                           ctx->cta_ids.p, ctx->cta_parts.p);
         mark(ctx, ST_FIXUP, st);
         uint32_t ns = 2 * grid;
+        // k_fixup merges the 2 boundary slots of every accumulate CTA in ONE CTA's shared memory: the grid above is capped in
+        // accmsm_init (acc_ctas_per_sm) so that they fit; a part with more SMs than that cap assumes must fail loudly, not overflow
+        if (ns > (uint32_t)(FIX_THREADS * FIX_PER_T)) return fail_arg(ctx, "msm: accumulate grid exceeds the fix-up kernel's slots");
         size_t smem2 = ns * (sizeof(xyzz_t) + sizeof(uint32_t));
         k_fixup<CURVE><<<1, FIX_THREADS, smem2, st>>>(ctx->cta_ids.p, ctx->cta_parts.p, ns, ctx->buckets.p);
         ctx->launches += 2;

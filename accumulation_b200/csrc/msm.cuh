@@ -33,6 +33,7 @@ constexpr uint32_t NONE_ID = 0xffffffffu;
 constexpr int ACC_THREADS = 256;       // threads per accumulate CTA
 constexpr int FIX_THREADS = 512;       // k_fixup: one CTA, FIX_PER_T slots per thread (<= 1536 slots fit in 227 KB)
 constexpr int FIX_PER_T = 3;
+static_assert((size_t)FIX_THREADS * FIX_PER_T * (sizeof(uint32_t) + 128) <= 227 * 1024, "k_fixup slots must fit in one CTA's shared memory");
 constexpr int MAX_WINDOWS = 64;
 constexpr int MAX_JOBS = 8;            // MSMs that share one pass of the pipeline (same key, same length)
 

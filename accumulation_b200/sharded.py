@@ -83,11 +83,17 @@ class ShardedMSM:
         self.ctx.msm_partial_dev(self.bases, d_scalars.data_ptr(), n, self.partial.data_ptr(), montgomery=montgomery, stream=st)
         return self._finish(st)
 
-    def msm_host(self, h_scalars, d_staging, montgomery: bool = True):
-        """h_scalars: pinned torch int64 tensor with this rank's scalar slice; d_staging: CUDA tensor of the same
-        shape.  H2D, local MSM, gather, combine; returns (xy, inf) on rank 0."""
-        d_staging.copy_(h_scalars, non_blocking=True)
-        return self.msm_dev(d_staging, montgomery=montgomery)
+    def msm_host(self, h_scalars, d_staging=None, montgomery: bool = True):
+        """h_scalars: pinned torch int64 tensor (or numpy array) with this rank's scalar slice in HOST memory.  The same
+        reference-facing C-ABI path as the single-GPU call: the library uploads the slice (second point segment in flight
+        while the first is accumulated) and leaves this rank's partial on the device (accmsm_msm_partial); then gather +
+        combine.  Returns (xy, inf) on rank 0.  d_staging is unused (kept for callers of the first version)."""
+        if self.world == 1:
+            arr = h_scalars.numpy().view(np.uint64) if hasattr(h_scalars, "numpy") else h_scalars
+            return self.ctx.msm(self.bases, arr, montgomery=montgomery, n=self.count)
+        ptr = h_scalars.data_ptr() if hasattr(h_scalars, "data_ptr") else np.ascontiguousarray(h_scalars, dtype=np.uint64).ctypes.data
+        self.ctx.msm_partial(self.bases, int(ptr), self.partial.data_ptr(), montgomery=montgomery, n=self.count)
+        return self._finish(_stream_handle())
 
     def ipa_final_key(self, challenges_mont, k: int):
         """final_key = cm_commit(key, h.compute_coeffs()) with the key sharded by point range: each GPU expands

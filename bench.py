@@ -217,7 +217,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: accumulation_b200 has no CPU path")
-    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 and not os.environ.get("ACCMSM_NO_AFFINITY") else None
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -258,7 +258,10 @@ def main():
         # digit kernel follows chunk by chunk, result read back); N > 1: pinned copy to the shard's GPU + partial + gather
         if world == 1:
             return ctx.msm(sh.bases, h_np, montgomery=False, n=count)
-        return sh.msm_host(h_sc, d_stage, montgomery=False)
+        if os.environ.get("ACCMSM_E2E_TORCH_COPY"):          # development switch: the first version's path (torch H2D copy + msm_partial_dev)
+            d_stage.copy_(h_sc, non_blocking=True)
+            return sh.msm_dev(d_stage, montgomery=False)
+        return sh.msm_host(h_sc, montgomery=False)           # accmsm_msm_partial with the same host pointer + gather + combine
 
     # ---- warm-up (also sizes the workspace) and parity of the thing being timed
     res = None
@@ -548,7 +551,7 @@ def main():
         t0 = time.perf_counter()
         exp = cref.msm_ark(0, pts, sc_np)
         dt = time.perf_counter() - t0
-        cpu = {"value": round(count / dt / 1e6, 4), "unit": "Mpts/s", "cores": ark_threads(count, cref.num_threads()), "kind": "port",
+        cpu = {"value": round(count / dt / 1e6, 4), "unit": "Mpts/s", "ms": round(dt * 1e3, 1), "cores": ark_threads(count, cref.num_threads()), "kind": "port",
                "sample": f"one full 2^{args.log_n}-point MSM (same bases and scalars as the GPU step), {dt:.2f} s"}
         if not args.no_verify:
             verified = bool(res[1] == exp[1] and np.array_equal(res[0], exp[0]) and np.array_equal(res_e2e[0], exp[0]))
