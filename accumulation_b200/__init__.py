@@ -197,6 +197,21 @@ class Context:
                                                  C.c_size_t(n), _p(out), C.byref(inf)), "msm_oneshot")
         return out, int(inf.value)
 
+    def msm_oneshot_batch(self, curve: int, bases_xy, scalars, montgomery: bool = True, infinity=None):
+        """m one-shot MSMs of equal length, each over its own bases, in shared passes: bases_xy (m, n, 8), scalars (m, n, 4),
+        infinity (m, n) or None -> (xy (m, 8), inf (m,)).  The succinct-check equations of all inputs of one ipa-pc-as prove."""
+        xy, sc = _u64(bases_xy), _u64(scalars)
+        if xy.ndim != 3 or sc.ndim != 3 or xy.shape[0] != sc.shape[0]:
+            raise ValueError("msm_oneshot_batch: bases (m, n, 8) and scalars (m, n, 4) expected")
+        m, n = xy.shape[0], min(xy.shape[1], sc.shape[1])
+        xy, sc = np.ascontiguousarray(xy[:, :n]), np.ascontiguousarray(sc[:, :n])
+        inf_in = None if infinity is None else np.ascontiguousarray(np.asarray(infinity, dtype=np.uint8).reshape(m, -1)[:, :n])
+        out = np.empty((m, 8), dtype=np.uint64)
+        inf = np.zeros(m, dtype=np.uint8)
+        self._check(self._lib.accmsm_msm_oneshot_batch(self._h, C.c_int(curve), _p(xy), _p(inf_in), _p(sc), C.c_int(int(montgomery)),
+                                                       C.c_size_t(n), C.c_size_t(m), _p(out), _p(inf)), "msm_oneshot_batch")
+        return out, inf
+
     def msm_ptr(self, bases: "Bases", host_ptr: int, n: int, montgomery: bool = True, offset: int = 0):
         """Same as msm() for a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
         out = np.empty(8, dtype=np.uint64)

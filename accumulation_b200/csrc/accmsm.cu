@@ -18,6 +18,7 @@
 #include "vec.cuh"
 #include "ipa.cuh"
 #include "wire.cuh"
+#include "hostfp.hpp"
 
 using namespace accmsm;
 
@@ -97,7 +98,12 @@ struct accmsm_ctx {
     DevBuf<uint32_t> sort_tile_count, sort_part_count, sort_part_offs;
     int segments_override = 0;                                  // development knob (ACCMSM_SEGMENTS): point segments of a large host-scalar MSM (1 = no pipelining)
     int seg0_pct = 12;                                          // share of the first of two segments (ACCMSM_SEG0_PCT)
+    std::vector<int> seg_pcts;                                  // development knob (ACCMSM_SEG_PCTS="12,60"): cumulative segment boundaries in percent
+    int seg_calls = 0;
+    bool skip_h2d = false, trace = false;                       // development knobs (ACCMSM_SKIP_H2D: timing experiments only -- reuses the scalars of the previous call; ACCMSM_TRACE)
+    std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
     int sort_lb_override = 0;                                   // development knob (ACCMSM_SORT_LB), 0 = automatic; -1 = first-version sort
+    DevBuf<uint8_t> oneshot_inf;
     DevBuf<affine_t> oneshot_xy, pair_pts[2];   // pair_pts / pair_off: ping-pong lists of the batch-affine rounds
     DevBuf<uint32_t> pair_off[2];
     DevBuf<uint8_t> pair_pref, pair_kinds, pair_tfac, pair_ctot, pair_cfac;
@@ -105,9 +111,11 @@ struct accmsm_ctx {
     DevBuf<xyzz_t> fold_partial;                // IpaPC::open folded-key materialisation (ipa.cuh)
     DevBuf<uint32_t> fold_flag;
     int ipa_fold_rounds = 5, ipa_fold_min_log = 14;   // accmsm_set_ipa_fold
-    affine_t *d_out_affine = nullptr;
-    uint32_t *d_out_inf = nullptr;
-    uint64_t *h_out = nullptr;   // pinned: 8 u64 affine + 1 u64 inf + 16 u64 partial
+    // Results that go back to the caller leave the device UN-NORMALISED (XYZZ, 128 B each) and are converted to affine by the
+    // host thread that receives them (hostfp.hpp: one inversion for all results of a call)
+    xyzz_t *d_out_raw = nullptr;
+    int out_curve = 0;           // curve of the sums in d_out_raw (set by msm_reduce / the combine entry points)
+    uint64_t *h_out = nullptr;   // pinned: MAX_JOBS x 16 u64 raw results + 64 u64 of small extras
     void *h_stage = nullptr;     // pinned staging for pageable host sources (upload())
     size_t stage_cap = 0;
     cudaEvent_t stage_done = nullptr;
@@ -168,6 +176,22 @@ void collect_timings(accmsm_ctx *ctx) {
         }
         prev = i;
     }
+    if (ctx->trace && !ctx->trace_ev.empty()) {      // ACCMSM_TRACE: timeline of the segments of a pipelined host-scalar MSM
+        for (auto &le : ctx->trace_ev) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->trace_ev[0].second, le.second) != cudaSuccess) (void)cudaGetLastError();
+            fprintf(stderr, "[accmsm trace] %8.3f ms  %s\n", ms, le.first.c_str());
+            if (&le != &ctx->trace_ev[0]) cudaEventDestroy(le.second);
+        }
+        cudaEventDestroy(ctx->trace_ev[0].second);
+        ctx->trace_ev.clear();
+    }
+}
+
+void trace_point(accmsm_ctx *ctx, cudaStream_t st, const std::string &label) {
+    if (!ctx->trace) return;
+    cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st);
+    ctx->trace_ev.push_back({label, ev});
 }
 
 // workspace ordering across streams (see accmsm_ctx::ws_done)
@@ -380,6 +404,7 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
         const size_t smem2 = ((size_t(1) << pl.lb) + pl.bucket_cap) * sizeof(uint32_t);
         if (smem1 > SORT_SMEM_OPT_IN || smem2 > SORT_SMEM_OPT_IN) return fail_arg(ctx, "msm: sort staging exceeds shared memory");
         mark(ctx, ST_DIGITS, st);
+        trace_point(ctx, st, "  sort begins");
         CU(ctx, cudaMemsetAsync(max_part, 0, sizeof(uint32_t), st));
         k_sort_tiles<Src, false><<<pl.ntiles, SORT_THREADS, smem0, st>>>(src, sh, B.d_inf, pl, 0u, pl.tiles_per_job, tile_count, tile_hist, nullptr, nullptr, gate);
         mark(ctx, ST_SCAN, st);
@@ -387,9 +412,11 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
         ctx->launches += 2;
         { int src2 = launch_scan(ctx, ctx->sort_part_count.p, pl.nparts, ctx->sort_part_offs.p, nullptr, st); if (src2) return src2; }
         mark(ctx, ST_SCATTER, st);
+        trace_point(ctx, st, "  counted + scanned");
         k_sort_tiles<Src, true><<<pl.ntiles, SORT_THREADS, smem1, st>>>(src, sh, B.d_inf, pl, 0u, pl.tiles_per_job, tile_count, tile_hist, ctx->sort_part_offs.p, ctx->sort_pairs.p, gate);
         k_sort_buckets<<<pl.nparts, SORT_BUCKET_THREADS, smem2, st>>>(ctx->sort_pairs.p, ctx->sort_part_offs.p, pl.lb, sh.nkeys, pl.bucket_cap, ctx->offsets.p, ctx->entries.p, gate);
         ctx->launches += 2;
+        trace_point(ctx, st, "  radix sort done");
     }
     {
         // first-version counting sort: the only sort of a short pass; behind the gate of a long one (its kernels return at
@@ -408,6 +435,7 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
         ctx->launches += 2;
     }
     mark(ctx, ST_ACCUMULATE, st);
+    trace_point(ctx, st, "  gated fallback sort passed");
     if (!into && sh.nkeys <= ACC_WARP_MAX_KEYS && n_entries <= ACC_WARP_MAX_ENTRIES) {
         // short MSM: one group of four replica warps per bucket, no slice merging (k_accumulate_warp_coop in msm.cuh)
         k_accumulate_warp_coop<CURVE><<<sh.nkeys, 128, 0, st>>>(ctx->offsets.p, sh.nkeys, ctx->entries.p, points, ctx->buckets.p);
@@ -460,6 +488,7 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
         else k_accumulate<CURVE, false><<<grid, ACC_THREADS, smem, st>>>(acc_offsets, sh.nkeys, acc_entries, acc_points, ctx->buckets.p,
                                                                           ctx->cta_ids.p, ctx->cta_parts.p);
         mark(ctx, ST_FIXUP, st);
+        trace_point(ctx, st, "  k_accumulate done");
         uint32_t ns = 2 * grid;
         // k_fixup merges the 2 boundary slots of every accumulate CTA in ONE CTA's shared memory: the grid above is capped in
         // accmsm_init (acc_ctas_per_sm) so that they fit; a part with more SMs than that cap assumes must fail loudly, not overflow
@@ -475,8 +504,9 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
 // last accumulated segment must not be used
 template <int CURVE>
 int msm_reduce(accmsm_ctx *ctx, const MsmShape &sh, bool use_offsets, const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial,
-               bool normalise, cudaStream_t st, affine_t *d_out_aff, uint32_t *d_out_inf) {
-    if (!d_out_aff) { d_out_aff = ctx->d_out_affine; d_out_inf = ctx->d_out_inf; }
+               bool normalise, cudaStream_t st, xyzz_t *d_out_raw) {
+    if (!d_out_raw) d_out_raw = ctx->d_out_raw;
+    ctx->out_curve = CURVE;
     const uint32_t nsets = sh.njobs * sh.sets_per_job;          // bucket sets to reduce
     const uint32_t *offs = use_offsets ? ctx->offsets.p : nullptr;
     mark(ctx, ST_REDUCE, st);
@@ -548,41 +578,40 @@ int msm_reduce(accmsm_ctx *ctx, const MsmShape &sh, bool use_offsets, const xyzz
         window_sums = sums;
     }
     mark(ctx, ST_FINISH, st);
-    k_finish<CURVE><<<sh.njobs, 32, 0, st>>>(window_sums, sh.sets_per_job, sh.c, d_extra, n_extra, normalise ? 1 : 0,
-                                             d_partial, d_out_aff, d_out_inf);
+    k_finish<CURVE><<<sh.njobs, 32, 0, st>>>(window_sums, sh.sets_per_job, sh.c, d_extra, n_extra, d_partial, normalise ? d_out_raw : nullptr);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     return ws_release(ctx, st);
 }
 
 // The whole pipeline over one segment.  Leaves the per-window sums combined into either a device partial (d_partial) or the
-// normalised affine result in ctx->d_out_affine / d_out_inf (or d_out_aff / d_out_inf).
+// un-normalised result in ctx->d_out_raw (or d_out_raw), which the host fetches and converts to affine.
 template <int CURVE, class Src>
 int run_msm(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const Src &src,
             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
-            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
+            xyzz_t *d_out_raw = nullptr) {
     MsmShape sh;
     int rc = msm_accumulate<CURVE>(ctx, B, jobs, n, n, src, false, st, &sh);
     if (rc) return rc;
-    return msm_reduce<CURVE>(ctx, sh, true, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+    return msm_reduce<CURVE>(ctx, sh, true, d_extra, n_extra, d_partial, normalise, st, d_out_raw);
 }
 
 // run_msm over scalar vectors resident in HBM (one pointer per job), dispatched on the key's curve
 int msm_mem(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, const uint8_t *const *d_scalars, int mont,
             const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st,
-            affine_t *d_out_aff = nullptr, uint32_t *d_out_inf = nullptr) {
+            xyzz_t *d_out_raw = nullptr) {
     if (B.curve == 0) {
         MemScalars<1> src; src.montgomery = mont;
         for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
-        return run_msm<0>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+        return run_msm<0>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_raw);
     }
     MemScalars<0> src; src.montgomery = mont;
     for (uint32_t j = 0; j < MAX_JOBS; j++) src.ptr[j] = j < jobs.njobs ? d_scalars[j] : nullptr;
-    return run_msm<1>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_aff, d_out_inf);
+    return run_msm<1>(ctx, B, jobs, n, src, d_extra, n_extra, d_partial, normalise, st, d_out_raw);
 }
 int msm_mem1(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint8_t *d_scalars, int mont,
              const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise, cudaStream_t st) {
-    return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr);
+    return msm_mem(ctx, B, MsmJobs(offset), n, &d_scalars, mont, d_extra, n_extra, d_partial, normalise, st, nullptr);
 }
 
 // Host -> device copy of a scalar / vector buffer.  Page-locked sources go straight to the DMA engine.  Pageable ones
@@ -671,15 +700,21 @@ int download(accmsm_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, cuda
     return ACCMSM_OK;
 }
 
-// normalised result -> host
+// k un-normalised results (XYZZ in device memory) -> host, affine conversion on the host (hostfp.hpp, one inversion)
+int fetch_points(accmsm_ctx *ctx, int curve, const xyzz_t *d_raw, size_t k, uint64_t *out_xy, uint8_t *out_inf, cudaStream_t st) {
+    if (k > MAX_JOBS) return fail_arg(ctx, "fetch_points: too many results");
+    CU(ctx, cudaMemcpyAsync(ctx->h_out, d_raw, k * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    hostfp::xyzz_to_affine(curve == 0 ? 0 : 1, ctx->h_out, k, out_xy, out_inf);
+    return ACCMSM_OK;
+}
+// the single result of the last pass -> host
 int fetch_affine(accmsm_ctx *ctx, uint64_t out_xy[8], uint8_t *out_inf, cudaStream_t st) {
     mark(ctx, ST_D2H, st);
-    CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, 64, cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaMemcpyAsync(ctx->h_out + 8, ctx->d_out_inf, 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_raw, sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
     mark(ctx, ST_COUNT, st);
     CU(ctx, cudaStreamSynchronize(st));
-    memcpy(out_xy, ctx->h_out, 64);
-    *out_inf = (uint8_t)(*(uint32_t *)(ctx->h_out + 8) != 0);
+    hostfp::xyzz_to_affine(ctx->out_curve == 0 ? 0 : 1, ctx->h_out, 1, out_xy, out_inf);
     collect_timings(ctx);
     return ACCMSM_OK;
 }
@@ -702,7 +737,7 @@ const Bases *find_bases(accmsm_ctx *ctx, uint64_t handle) {
 
 // MSM of host scalars, one vector: uploads and enqueues on the ctx stream.  d_extra/n_extra: XYZZ partials added before
 // normalisation.  d_partial (nullable): where the un-normalised sum goes (DEVICE memory, possibly a peer GPU's);
-// normalise: the affine image goes to ctx->d_out_affine.  The caller fetches / synchronises.
+// normalise: the result goes to ctx->d_out_raw (XYZZ; fetch_affine converts it on the host).  The caller fetches / synchronises.
 //
 // Large vectors (>= 16 MiB) hide the PCIe transfer behind the arithmetic: the points are cut into two segments of about
 // 1/8 and 7/8 of the vector (measured best of 12 / 25 / 37 %: profiles/r02i_*; the accumulation of a segment takes ~4x as long as the upload of the same number of
@@ -759,14 +794,15 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
             }
             from = stage + off;
         }
-        CU(ctx, cudaMemcpyAsync(ctx->scalars.p + off, from, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (!ctx->skip_h2d || ctx->seg_calls == 0) CU(ctx, cudaMemcpyAsync(ctx->scalars.p + off, from, len, cudaMemcpyHostToDevice, ctx->copy_stream));
         CU(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
         return ACCMSM_OK;
     };
     // segment boundaries on chunk boundaries
     const int nseg = ctx->segments_override > 1 ? ctx->segments_override : 2;
     std::vector<uint32_t> seg_end;       // in chunks
-    if (nseg == 2) { seg_end.push_back(std::max(1u, (nchunks * (uint32_t)ctx->seg0_pct + 50) / 100)); seg_end.push_back(nchunks); }
+    if (!ctx->seg_pcts.empty()) { for (int pc : ctx->seg_pcts) seg_end.push_back(std::max(1u, (nchunks * (uint32_t)pc + 50) / 100)); seg_end.push_back(nchunks); }
+    else if (nseg == 2) { seg_end.push_back(std::max(1u, (nchunks * (uint32_t)ctx->seg0_pct + 50) / 100)); seg_end.push_back(nchunks); }
     else for (int g = 1; g <= nseg; g++) seg_end.push_back(std::max<uint32_t>(g, (uint32_t)((uint64_t)nchunks * g / nseg)));
     seg_end.back() = nchunks;
     MsmShape sh;
@@ -775,12 +811,15 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
         CU(ctx, ctx->buckets.ensure(s0.nkeys));
         CU(ctx, cudaMemsetAsync(ctx->buckets.p, 0, (size_t)s0.nkeys * sizeof(xyzz_t), st));
     }
+    auto tr = [&](const std::string &label) { trace_point(ctx, st, label); };
+    tr("start");
     uint32_t c0 = 0;
     for (size_t g = 0; g < seg_end.size(); g++) {
         const uint32_t c1 = std::min(seg_end[g], nchunks);
         if (c1 <= c0) continue;
         for (uint32_t c = c0; c < c1; c++) { int frc = feed(c); if (frc) return frc; }
         CU(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[c1 - 1], 0));
+        tr("seg" + std::to_string(g) + " arrived (chunks " + std::to_string(c0) + ".." + std::to_string(c1) + ")");
         const size_t e0 = (size_t)c0 * chunk_elems, e1 = std::min<size_t>(n, (size_t)c1 * chunk_elems);
         const uint8_t *ptr = ctx->scalars.p + e0 * 32;
         int rc;
@@ -789,16 +828,20 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
         else { MemScalars<0> ms; ms.montgomery = mont; for (uint32_t j = 0; j < MAX_JOBS; j++) ms.ptr[j] = j ? nullptr : ptr;
                rc = msm_accumulate<1>(ctx, B, MsmJobs(offset + e0), e1 - e0, n, ms, true, st, &sh); }
         if (rc) return rc;
+        tr("seg" + std::to_string(g) + " accumulated");
         c0 = c1;
     }
     if (pageable) { CU(ctx, cudaEventRecord(ctx->stage_done, ctx->copy_stream)); ctx->stage_busy = true; }
-    if (B.curve == 0) return msm_reduce<0>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr);
-    return msm_reduce<1>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr, nullptr);
+    ctx->seg_calls++;
+    const int rrc = B.curve == 0 ? msm_reduce<0>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr)
+                                 : msm_reduce<1>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr);
+    tr("reduced");
+    return rrc;
 }
 
 // identity partial(s) into d_out[0..k)
 template <int CURVE> void launch_identity_partials(accmsm_ctx *ctx, xyzz_t *d_out, uint32_t k, cudaStream_t st) {
-    k_finish<CURVE><<<k, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, d_out, nullptr, nullptr);
+    k_finish<CURVE><<<k, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, d_out, nullptr);
     ctx->launches++;
 }
 
@@ -834,13 +877,10 @@ int msm_rows_host(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, size
         if (rc) return rc;
         if (out_xy) {
             mark(ctx, ST_D2H, st);
-            CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, jobs.njobs * 64, cudaMemcpyDeviceToHost, st));
-            CU(ctx, cudaMemcpyAsync(ctx->h_out + 8 * MAX_JOBS, ctx->d_out_inf, jobs.njobs * 4, cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_raw, jobs.njobs * sizeof(xyzz_t), cudaMemcpyDeviceToHost, st));
             mark(ctx, ST_COUNT, st);
             CU(ctx, cudaStreamSynchronize(st));
-            memcpy(out_xy + 8 * j0, ctx->h_out, jobs.njobs * 64);
-            const uint32_t *inf = (const uint32_t *)(ctx->h_out + 8 * MAX_JOBS);
-            for (uint32_t j = 0; j < jobs.njobs; j++) out_inf[j0 + j] = inf[j] != 0;
+            hostfp::xyzz_to_affine(B.curve == 0 ? 0 : 1, ctx->h_out, jobs.njobs, out_xy + 8 * j0, out_inf + j0);
         }
     }
     if (!out_xy) { mark(ctx, ST_COUNT, st); CU(ctx, cudaStreamSynchronize(st)); }
@@ -909,6 +949,9 @@ int accmsm_init(accmsm_ctx **out, int device) {
     if (const char *e = getenv("ACCMSM_SORT_LB")) ctx->sort_lb_override = atoi(e);
     if (const char *e = getenv("ACCMSM_SEGMENTS")) ctx->segments_override = atoi(e);
     if (const char *e = getenv("ACCMSM_SEG0_PCT")) ctx->seg0_pct = std::min(90, std::max(1, atoi(e)));
+    if (const char *e = getenv("ACCMSM_SEG_PCTS")) { for (const char *q = e; *q;) { ctx->seg_pcts.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; } }
+    if (const char *e = getenv("ACCMSM_SKIP_H2D")) ctx->skip_h2d = atoi(e) != 0;
+    if (const char *e = getenv("ACCMSM_TRACE")) ctx->trace = atoi(e) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
@@ -917,9 +960,8 @@ int accmsm_init(accmsm_ctx **out, int device) {
     cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ws_done, cudaEventDisableTiming);
     for (int i = 0; i < accmsm_ctx::ARG_SLOTS; i++) cudaEventCreateWithFlags(&ctx->arg_done[i], cudaEventDisableTiming);
-    bool ok = cudaMallocHost(&ctx->h_args, accmsm_ctx::ARG_SLOTS * accmsm_ctx::ARG_SLOT_BYTES) == cudaSuccess && cudaMalloc(&ctx->d_out_affine, MAX_JOBS * sizeof(affine_t)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_out_inf, MAX_JOBS * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMallocHost(&ctx->h_out, (MAX_JOBS * 9 + 32) * sizeof(uint64_t)) == cudaSuccess;
+    bool ok = cudaMallocHost(&ctx->h_args, accmsm_ctx::ARG_SLOTS * accmsm_ctx::ARG_SLOT_BYTES) == cudaSuccess && cudaMalloc(&ctx->d_out_raw, MAX_JOBS * sizeof(xyzz_t)) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_out, (MAX_JOBS * 16 + 64) * sizeof(uint64_t)) == cudaSuccess;
     // shared-memory opt-in and resident CTAs per SM for the accumulate kernels
     size_t smem = 2 * ACC_THREADS * (sizeof(xyzz_t) + sizeof(uint32_t));
     size_t smem_fix = (size_t)FIX_THREADS * FIX_PER_T * (sizeof(xyzz_t) + sizeof(uint32_t));
@@ -974,14 +1016,13 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     for (auto &b : ctx->vec_cache) cudaFree(b.first);
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
-    ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release();
+    ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release(); ctx->oneshot_inf.release();
     ctx->sort_pairs.release(); ctx->sort_tile_count.release(); ctx->sort_part_count.release(); ctx->sort_part_offs.release();
     for (int i = 0; i < 2; i++) { ctx->pair_pts[i].release(); ctx->pair_off[i].release(); }
     ctx->fold_partial.release(); ctx->fold_flag.release();
     ctx->pair_pref.release(); ctx->pair_kinds.release(); ctx->pair_tfac.release(); ctx->pair_ctot.release(); ctx->pair_cfac.release();
     for (int i = 0; i < 2; i++) { ctx->red_sum[i].release(); ctx->red_wsum[i].release(); }
-    if (ctx->d_out_affine) cudaFree(ctx->d_out_affine);
-    if (ctx->d_out_inf) cudaFree(ctx->d_out_inf);
+    if (ctx->d_out_raw) cudaFree(ctx->d_out_raw);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);
@@ -1178,6 +1219,53 @@ int accmsm_msm_oneshot(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, con
     return fetch_affine(ctx, out_xy, out_inf, st);
 }
 
+// m independent one-shot MSMs of the same length n, each over its OWN bases (bases_xy: m x n x 8 u64, scalars: m x n x 4 u64,
+// infinity: m x n bytes or NULL): the succinct-check group equations of all inputs and accumulators of one
+// AtomicASForInnerProductArgPC::prove / verify (src/ipa_pc_as/mod.rs:198-205 is called once per input, :262-270 / :625-640
+// loop over them; 2k + 3 terms each).  Up to MAX_JOBS of them share one pass of the pipeline, so the latency-bound tail of a
+// short MSM (bucket reduction, Horner over the windows) is paid once per pass, not once per equation.
+int accmsm_msm_oneshot_batch(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, const uint8_t *infinity, const uint64_t *scalars,
+                             int scalars_montgomery, size_t n, size_t m, uint64_t *out_xy, uint8_t *out_inf) {
+    if (!ctx || (m && (!out_xy || !out_inf)) || (curve != 0 && curve != 1) || (n && m && (!bases_xy || !scalars)) ||
+        n >= (size_t(1) << 31) || m >= (size_t(1) << 20) || n * m >= (size_t(1) << 31))
+        return fail_arg(ctx, "msm_oneshot_batch: bad argument");
+    if (is_group(ctx)) return accmsm_msm_oneshot_batch(ctx->kids[0], curve, bases_xy, infinity, scalars, scalars_montgomery, n, m, out_xy, out_inf);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (m == 0) return ACCMSM_OK;
+    if (n == 0) { for (size_t j = 0; j < m; j++) write_identity(ctx, curve, out_xy + 8 * j, out_inf + j); return ACCMSM_OK; }
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    clear_marks(ctx);
+    CU(ctx, ctx->scalars.ensure(m * n * 32));
+    CU(ctx, ctx->oneshot_xy.ensure(m * n));
+    mark(ctx, ST_H2D, st);
+    { int urc = upload(ctx, ctx->oneshot_xy.p, bases_xy, m * n * sizeof(affine_t), st); if (urc) return urc; }
+    { int urc = upload(ctx, ctx->scalars.p, scalars, m * n * 32, st); if (urc) return urc; }
+    Bases B;
+    B.curve = curve; B.n = m * n; B.d_xy = ctx->oneshot_xy.p;
+    bool any_inf = false;
+    if (infinity) for (size_t i = 0; i < m * n && !any_inf; i++) any_inf = infinity[i] != 0;
+    if (any_inf) {
+        CU(ctx, ctx->oneshot_inf.ensure(m * n));
+        { int urc = upload(ctx, ctx->oneshot_inf.p, infinity, m * n, st); if (urc) return urc; }
+        B.d_inf = ctx->oneshot_inf.p;
+    }
+    for (size_t j0 = 0; j0 < m; j0 += MAX_JOBS) {
+        MsmJobs jobs;
+        jobs.njobs = (uint32_t)std::min<size_t>(MAX_JOBS, m - j0);
+        const uint8_t *ptrs[MAX_JOBS];
+        for (uint32_t j = 0; j < jobs.njobs; j++) { jobs.offset[j] = (j0 + j) * n; ptrs[j] = ctx->scalars.p + (j0 + j) * n * 32; }
+        int rc = msm_mem(ctx, B, jobs, n, ptrs, scalars_montgomery, nullptr, 0, nullptr, true, st);
+        if (rc) return rc;
+        mark(ctx, ST_D2H, st);
+        rc = fetch_points(ctx, curve, ctx->d_out_raw, jobs.njobs, out_xy + 8 * j0, out_inf + j0, st);
+        if (rc) return rc;
+    }
+    mark(ctx, ST_COUNT, st);
+    collect_timings(ctx);
+    return ACCMSM_OK;
+}
+
 int accmsm_msm_batch(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, size_t k, const uint64_t *scalars,
                      int scalars_montgomery, uint64_t *out_xy, uint8_t *out_inf) {
     if (!ctx || (k && (!out_xy || !out_inf)) || (n && k && !scalars)) return fail_arg(ctx, "msm_batch: bad argument");
@@ -1238,8 +1326,8 @@ int accmsm_msm_partial_dev(accmsm_ctx *ctx, uint64_t handle, size_t offset, size
     int rc;
     if (n == 0) {
         { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
-        if (B->curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, (xyzz_t *)d_out_partial, nullptr, nullptr);
-        else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, 0, (xyzz_t *)d_out_partial, nullptr, nullptr);
+        if (B->curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, (xyzz_t *)d_out_partial, nullptr);
+        else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, nullptr, 0, (xyzz_t *)d_out_partial, nullptr);
         ctx->launches++;
         rc = ws_release(ctx, st);
     } else {
@@ -1284,8 +1372,9 @@ int accmsm_combine_partials_dev(accmsm_ctx *ctx, int curve, const void *d_partia
     // stage marks of a preceding accmsm_*_partial_dev on the same stream are kept (bench.py reads them)
     { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
     mark(ctx, ST_FINISH, st);
-    if (curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
-    else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, 1, nullptr, ctx->d_out_affine, ctx->d_out_inf);
+    if (curve == 0) k_finish<0><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, nullptr, ctx->d_out_raw);
+    else k_finish<1><<<1, 32, 0, st>>>(nullptr, 0, 1, (const xyzz_t *)d_partials, (uint32_t)k, nullptr, ctx->d_out_raw);
+    ctx->out_curve = curve;
     ctx->launches++;
     return fetch_affine(ctx, out_xy, out_inf, st);
 }
@@ -1299,16 +1388,11 @@ int accmsm_combine_partials_batch_dev(accmsm_ctx *ctx, int curve, const void *d_
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
-    if (curve == 0) k_combine_batch<0><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_affine, ctx->d_out_inf);
-    else k_combine_batch<1><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_affine, ctx->d_out_inf);
+    if (curve == 0) k_combine_batch<0><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_raw);
+    else k_combine_batch<1><<<(uint32_t)m, 32, 0, st>>>((const xyzz_t *)d_partials, (uint32_t)k, (uint32_t)m, ctx->d_out_raw);
+    ctx->out_curve = curve;
     ctx->launches++;
-    CU(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out_affine, m * 64, cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaMemcpyAsync(ctx->h_out + 8 * MAX_JOBS, ctx->d_out_inf, m * 4, cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
-    memcpy(out_xy, ctx->h_out, m * 64);
-    const uint32_t *inf = (const uint32_t *)(ctx->h_out + 8 * MAX_JOBS);
-    for (size_t j = 0; j < m; j++) out_inf[j] = inf[j] != 0;
-    return ACCMSM_OK;
+    return fetch_points(ctx, curve, ctx->d_out_raw, m, out_xy, out_inf, st);
 }
 
 static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_mont, int k, size_t coeff_offset, size_t n,

@@ -1008,13 +1008,11 @@ __global__ void __launch_bounds__(256) k_leaf_combine_coop(const xyzz_t *__restr
     }
 }
 
-// k_finish (one CTA per job): out = sum_w 2^(c w) S_w (+ optional extra partials), then either the raw XYZZ
-// partial (multi-GPU: partials are gathered and combined later) or the normalised affine image.
+// k_finish (one CTA per job): out = sum_w 2^(c w) S_w (+ optional extra partials), left as an un-normalised XYZZ sum.
 template <int CURVE>
 __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, uint32_t c,
-                         const xyzz_t *__restrict__ extra, uint32_t n_extra, int normalise,
-                         xyzz_t *__restrict__ out_partial, affine_t *__restrict__ out_affine,
-                         uint32_t *__restrict__ out_inf) {
+                         const xyzz_t *__restrict__ extra, uint32_t n_extra,
+                         xyzz_t *__restrict__ out_partial, xyzz_t *__restrict__ out_raw) {
     using Cv = Curve<CURVE>;      // loops over one dbl / one sqr-mul body: already instruction-cache friendly
     if (threadIdx.x != 0) return;
     const uint32_t job = blockIdx.x;
@@ -1026,29 +1024,22 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
         Cv::add(acc, s);
     }
     for (uint32_t i = 0; i < n_extra; i++) { xyzz_t s = load_xyzz(extra + (size_t)job * n_extra + i); Cv::add(acc, s); }
+    // out_partial: a share for a later combine (possibly a peer GPU's memory); out_raw: the result the host fetches and converts
+    // to affine itself (hostfp.hpp) -- the single inversion of an MSM does not run on one GPU thread any more
     if (out_partial) store_xyzz(out_partial + job, acc);
-    if (normalise) {
-        affine_t a; uint32_t inf;
-        Cv::template to_affine<true>(acc, a, inf);
-        store_fe(&out_affine[job].x, a.x); store_fe(&out_affine[job].y, a.y);
-        out_inf[job] = inf;
-    }
+    if (out_raw) store_xyzz(out_raw + job, acc);
 }
 
-// out[j] = normalise(sum_r partials[r * m + j]), j < m: the G-way add after an all-gather of m shares per rank
-// (rank-major, as the gather leaves them).  One CTA per output, one thread (G <= 16 additions + one inversion).
+// out[j] = sum_r partials[r * m + j], j < m: the G-way add after an all-gather of m shares per rank (rank-major, as the
+// gather leaves them).  One CTA per output, one thread (G <= 16 additions); the host normalises.
 template <int CURVE>
-__global__ void k_combine_batch(const xyzz_t *__restrict__ partials, uint32_t k, uint32_t m,
-                                affine_t *__restrict__ out_affine, uint32_t *__restrict__ out_inf) {
+__global__ void k_combine_batch(const xyzz_t *__restrict__ partials, uint32_t k, uint32_t m, xyzz_t *__restrict__ out_raw) {
     using Cv = Curve<CURVE>;
     if (threadIdx.x != 0) return;
     const uint32_t j = blockIdx.x;
     xyzz_t acc = Cv::identity();
     for (uint32_t r = 0; r < k; r++) { xyzz_t s = load_xyzz(partials + (size_t)r * m + j); Cv::add(acc, s); }
-    affine_t a; uint32_t inf;
-    Cv::template to_affine<true>(acc, a, inf);
-    store_fe(&out_affine[j].x, a.x); store_fe(&out_affine[j].y, a.y);
-    out_inf[j] = inf;
+    store_xyzz(out_raw + j, acc);
 }
 
 // ------------------------------------------------------------------------------------------------

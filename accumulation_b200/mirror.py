@@ -144,6 +144,37 @@ class InnerProductArgPC:
         return bool(res_inf)
 
     @staticmethod
+    def succinct_check_terms(curve: int, comm, point, value, l_vec, r_vec, round_challenges, h_prime_xy, final_comm_key_xy, c):
+        """(bases (2k + 3, 8), infinity flags, canonical scalars (2k + 3, 4)) of the equation above"""
+        from . import scalar_field
+        f = scalar_field(curve)
+        m = _MODULI[f]
+        xis = [_fe_to_int(f, x) for x in np.asarray(round_challenges, dtype=np.uint64).reshape(-1, 4)]
+        k = len(xis)
+        z, v, cc = _fe_to_int(f, point), _fe_to_int(f, value), _fe_to_int(f, c)
+        hz = 1
+        for i, xi in enumerate(xis, start=1):
+            hz = hz * (1 + xi * pow(z, 1 << (k - i), m)) % m
+        bases = [np.asarray(comm[0], dtype=np.uint64)] + [np.asarray(p[0], dtype=np.uint64) for p in l_vec] + \
+                [np.asarray(p[0], dtype=np.uint64) for p in r_vec] + [np.asarray(h_prime_xy, dtype=np.uint64), np.asarray(final_comm_key_xy, dtype=np.uint64)]
+        inf = [int(comm[1])] + [int(p[1]) for p in l_vec] + [int(p[1]) for p in r_vec] + [0, 0]
+        scal = [1] + [pow(xi, -1, m) for xi in xis] + xis + [(v - hz * cc) % m, (-cc) % m]
+        sc = np.array([[(s_ >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for s_ in scal], dtype=np.uint64)
+        return np.array(bases), np.array(inf, dtype=np.uint8), sc
+
+    @staticmethod
+    def succinct_check_equations(ctx, curve: int, instances) -> list:
+        """The equations of ALL inputs and accumulators of one prove / verify (the loops at src/ipa_pc_as/mod.rs:262-270 and
+        :625-640 call succinct_check once per instance) as ONE batched call (accmsm_msm_oneshot_batch): `instances` is a list
+        of argument tuples of succinct_check_equation (without ctx and curve), all of the same degree."""
+        terms = [InnerProductArgPC.succinct_check_terms(curve, *inst) for inst in instances]
+        if not terms:
+            return []
+        _, inf = ctx.msm_oneshot_batch(curve, np.stack([t[0] for t in terms]), np.stack([t[2] for t in terms]), montgomery=False,
+                                       infinity=np.stack([t[1] for t in terms]))
+        return [bool(x) for x in inf]
+
+    @staticmethod
     def check_final_key(vk: CommitterKey, check_poly_challenges, final_comm_key_xy, final_comm_key_inf: int = 0) -> bool:
         """Tail of check_individual_opening_challenges (reached from decide, src/ipa_pc_as/mod.rs:836-845):
         final_key = cm_commit(vk.comm_key, h.compute_coeffs()); accept iff final_key == proof.final_comm_key."""

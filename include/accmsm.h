@@ -123,6 +123,13 @@ int accmsm_msm(accmsm_ctx *ctx, uint64_t handle, size_t offset, size_t n, const 
  * (src/hp_as/mod.rs:391-406, src/ipa_pc_as/mod.rs:322-343).  bases_xy: n x 8, infinity: n bytes or NULL. */
 int accmsm_msm_oneshot(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, const uint8_t *infinity,
                        const uint64_t *scalars, int scalars_montgomery, size_t n, uint64_t out_xy[8], uint8_t *out_inf);
+/* m such one-shot MSMs of equal length n, each over its own bases, in shared passes of the pipeline (up to 8 per pass): the
+ * succinct-check group equations of every input and accumulator of one ipa-pc-as prove / verify (IpaPC::succinct_check is
+ * called once per input instance: src/ipa_pc_as/mod.rs:198-205 inside the loops at :262-270 and :625-640; 2k + 3 terms each).
+ * bases_xy: m x n x 8, infinity: m x n bytes or NULL, scalars: m x n x 4, out_xy: m x 8, out_inf: m. */
+int accmsm_msm_oneshot_batch(accmsm_ctx *ctx, int curve, const uint64_t *bases_xy, const uint8_t *infinity,
+                             const uint64_t *scalars, int scalars_montgomery, size_t n, size_t m, uint64_t *out_xy,
+                             uint8_t *out_inf);
 /* k scalar vectors over the same bases (hp_as::decide commits a, b, a∘b: src/hp_as/mod.rs:910-918;
  * NARK prove commits z_A, z_B, z_C: src/r1cs_nark_as/r1cs_nark/mod.rs:216-218).
  * scalars: k x n x 4 u64, out_xy: k x 8, out_inf: k. */

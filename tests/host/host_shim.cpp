@@ -60,3 +60,16 @@ template <int C> static void ec_sum(const uint32_t *xy, const uint8_t *neg, size
 extern "C" void host_ec_sum(int curve, const uint32_t *xy, const uint8_t *neg, size_t n, int mode, uint32_t *out_xy, uint8_t *out_inf) {
     if (curve == 0) ec_sum<0>(xy, neg, n, mode, out_xy, out_inf); else ec_sum<1>(xy, neg, n, mode, out_xy, out_inf);
 }
+
+// the library's host-side 4 x 64-bit field code (hostfp.hpp): products, inversion, XYZZ -> affine with one inversion
+#include "../../accumulation_b200/csrc/hostfp.hpp"
+extern "C" void host_fast_op(int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) {
+    const hostfp::Modulus &M = hostfp::modulus(field);
+    for (size_t i = 0; i < n; i++) {
+        if (op == 0) hostfp::mul(M, a + 4 * i, b + 4 * i, o + 4 * i);
+        else hostfp::inv(M, a + 4 * i, o + 4 * i);
+    }
+}
+extern "C" void host_fast_xyzz_to_affine(int field, const uint64_t *raw, size_t k, uint64_t *out_xy, uint8_t *out_inf) {
+    hostfp::xyzz_to_affine(field, raw, k, out_xy, out_inf);
+}

@@ -93,6 +93,9 @@ def test_ipa_open_vs_oracle_and_verifies(ctx, curve, k, precompute):
         v_bad = v.copy(); v_bad[0] ^= np.uint64(1)
         assert not ab.InnerProductArgPC.succinct_check_equation(ctx, curve, comm, z, v_bad, l_vec, r_vec, xs, hp, fk, c)
         assert not ab.InnerProductArgPC.succinct_check_equation(ctx, curve, comm, z, v, r_vec, l_vec, xs, hp, fk, c)
+        # all instances of a prove / verify in ONE batched call: accept, reject, accept
+        good, bad_inst = (comm, z, v, l_vec, r_vec, xs, hp, fk, c), (comm, z, v_bad, l_vec, r_vec, xs, hp, fk, c)
+        assert ab.InnerProductArgPC.succinct_check_equations(ctx, curve, [good, bad_inst, good]) == [True, False, True]
         # the decider's half of check(): final_key == cm_commit(key, h.compute_coeffs())  (GPU, fused K3 -> K2)
         assert ab.InnerProductArgPC.check_final_key(ck, xs, fk, 0)
         bad = fk.copy(); bad[3] ^= np.uint64(2)

@@ -362,6 +362,33 @@ def test_msm_oneshot_unregistered_bases(ctx, curve, n):
         assert same_point(ctx.msm_oneshot(curve, pts, scm[: max(n - 1, 0)]), cref.msm_ark(curve, pts[: n - 1], sc[: n - 1]) if n > 1 else point_result(curve, None))
 
 
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("n,m", [(0, 3), (1, 1), (43, 3), (39, 11), (300, 8), (5000, 2)])
+def test_msm_oneshot_batch(ctx, curve, n, m):
+    """m one-shot MSMs of equal length over their own bases in shared passes (the succinct-check equations of all inputs of
+    one ipa-pc-as prove: 2 k + 3 terms each, 43 at k = 20): every result equals the single-call result and the oracle's;
+    m > 8 spans several passes; identity bases and Montgomery-form scalars as in the single call"""
+    sf = cref.scalar_field(curve)
+    pts = cref.gen_points(curve, 1300 + n, max(n * m, 1))[: n * m].reshape(m, n, 8)
+    sc = cref.gen_scalars(sf, 1301 + n, n * m, False).reshape(m, n, 4)
+    if n and m > 1:
+        sc[1, 0] = 0                                      # a zero scalar, a scalar == 1 (ark's shortcut), a repeated base
+        sc[1, n - 1] = cref.from_int(1)
+        pts[m - 1, n - 1] = pts[m - 1, 0]
+    inf = ((np.arange(n * m) % 7) == 2).astype(np.uint8).reshape(m, n)
+    xy, oinf = ctx.msm_oneshot_batch(curve, pts, sc, montgomery=False)
+    assert xy.shape == (m, 8) and oinf.shape == (m,)
+    for j in range(m):
+        exp = cref.msm_ark(curve, pts[j], sc[j]) if n else point_result(curve, None)
+        assert same_point((xy[j], int(oinf[j])), exp)
+        if n:
+            assert same_point((xy[j], int(oinf[j])), ctx.msm_oneshot(curve, pts[j], sc[j], montgomery=False))
+    if n:
+        xy2, oinf2 = ctx.msm_oneshot_batch(curve, pts, cref.to_mont(sf, sc.reshape(-1, 4)).reshape(m, n, 4), montgomery=True, infinity=inf)
+        for j in range(m):
+            assert same_point((xy2[j], int(oinf2[j])), cref.msm_ark(curve, pts[j], sc[j], bases_inf=inf[j]))
+
+
 def test_pinned_host_buffers(ctx, keys):
     """accmsm_host_alloc: page-locked scalar buffers give the same result (and the PCIe-rate H2D path)"""
     pts, B = keys[0]

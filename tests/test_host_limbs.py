@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "host", "libhostshim.so")
 
 @pytest.fixture(scope="module")
 def shim():
-    deps = [SRC, os.path.join(HERE, "..", "accumulation_b200", "csrc", "fp.cuh"), os.path.join(HERE, "..", "accumulation_b200", "csrc", "ec.cuh")]
+    deps = [SRC] + [os.path.join(HERE, "..", "accumulation_b200", "csrc", f) for f in ("fp.cuh", "ec.cuh", "hostfp.hpp")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO, SRC])
     return C.CDLL(SO)
@@ -119,3 +119,53 @@ def test_xyzz_group_law(shim, curve):
     got, ginf = ec_sum(shim, curve, np.repeat(P, 20, axis=0), None, 3)   # 20 doublings of P
     exp, einf = cref.point_mul(curve, P[0], 0, cref.from_int(1 << 20))
     assert ginf == 0 and (got == exp).all()
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_library_host_field_code(shim, field):
+    """hostfp.hpp (4 x 64-bit limbs; the library's host thread uses it for the affine conversion of returned sums and for the
+    inverse of an IpaPC::open round challenge) against the oracle: products, inverses, XYZZ -> affine with one inversion."""
+    m = [pyref.P_PALLAS_BASE, pyref.Q_PALLAS_SCALAR][field]
+    n = 3000
+    a = cref.gen_scalars(field, 11, n, True)
+    b = cref.gen_scalars(field, 12, n, True)
+    edge = cref.ints_to_arr([0, 1, m - 1, (1 << 256) % m, m - 2, 2, (1 << 255) % m, 0xffffffff, 1 << 32, m >> 1, (1 << 254) - 1, m - (1 << 32)])
+    ea, eb = np.repeat(edge, len(edge), axis=0), np.tile(edge, (len(edge), 1))
+    a, b = np.concatenate([a, ea]), np.concatenate([b, eb])
+
+    def fast(op, x, y=None):
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        out = np.empty_like(x)
+        yp = None if y is None else np.ascontiguousarray(y, dtype=np.uint64).ctypes.data_as(C.c_void_p)
+        shim.host_fast_op(C.c_int(field), C.c_int(op), x.ctypes.data_as(C.c_void_p), yp, out.ctypes.data_as(C.c_void_p), C.c_size_t(x.shape[0]))
+        return out
+
+    assert (fast(0, a, b) == cref.fe_mul(field, a, b)).all()
+    inv = fast(1, a[:400])
+    one = cref.to_mont(field, cref.ints_to_arr([1]))[0]
+    prod = cref.fe_mul(field, inv, a[:400])
+    assert all((p == one).all() for p in prod)
+    assert (fast(1, cref.ints_to_arr([0])) == 0).all()                       # inv(0) = 0, like the device code
+    # XYZZ -> affine: points (x, y) scaled by random z (X = x z^2, Y = y z^3, ZZ = z^2, ZZZ = z^3), identities in between
+    k = 37
+    curve = field
+    pts = cref.gen_points(curve, 21 + curve, k)
+    z = cref.gen_scalars(field, 13, k, True)
+    zz = cref.fe_mul(field, z, z)
+    zzz = cref.fe_mul(field, zz, z)
+    raw = np.zeros((k, 16), dtype=np.uint64)
+    raw[:, 0:4] = cref.fe_mul(field, pts[:, 0:4], zz)
+    raw[:, 4:8] = cref.fe_mul(field, pts[:, 4:8], zzz)
+    raw[:, 8:12], raw[:, 12:16] = zz, zzz
+    ident = [0, 5, 36]
+    for i in ident:
+        raw[i, 8:16] = 0
+    for kk in (1, 2, k):          # the batch sizes share one inversion
+        out = np.empty((kk, 8), dtype=np.uint64)
+        inf = np.empty(kk, dtype=np.uint8)
+        shim.host_fast_xyzz_to_affine(C.c_int(field), raw.ctypes.data_as(C.c_void_p), C.c_size_t(kk), out.ctypes.data_as(C.c_void_p), inf.ctypes.data_as(C.c_void_p))
+        for i in range(kk):
+            if i in ident:
+                assert inf[i] == 1 and (out[i, :4] == 0).all() and (out[i, 4:] == one).all()     # ark's identity image (0, 1, true)
+            else:
+                assert inf[i] == 0 and (out[i] == pts[i]).all()
