@@ -123,7 +123,7 @@ class Context:
     def set_window_bits(self, c: int):
         self._check(self._lib.accmsm_set_window_bits(self._h, C.c_int(c)), "set_window_bits")
 
-    def set_ipa_fold(self, rounds: int = 5, min_log_n: int = 14):
+    def set_ipa_fold(self, rounds: int = 5, min_log_n: int = 11):
         """IpaPC::open: materialise the folded key every `rounds` rounds while the current key has >= 2^min_log_n
         points (0 = never); results are identical either way."""
         self._check(self._lib.accmsm_set_ipa_fold(self._h, C.c_int(rounds), C.c_int(min_log_n)), "set_ipa_fold")

@@ -100,6 +100,7 @@ struct accmsm_ctx {
     int seg0_pct = 12;                                          // share of the first of two segments (ACCMSM_SEG0_PCT)
     std::vector<int> seg_pcts;                                  // development knob (ACCMSM_SEG_PCTS="12,60"): cumulative segment boundaries in percent
     int seg_calls = 0;
+    bool no_coop_precompute = false;                            // development knob (ACCMSM_NO_COOP_PRECOMPUTE)
     bool skip_h2d = false, trace = false;                       // development knobs (ACCMSM_SKIP_H2D: timing experiments only -- reuses the scalars of the previous call; ACCMSM_TRACE)
     std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
     int sort_lb_override = 0;                                   // development knob (ACCMSM_SORT_LB), 0 = automatic; -1 = first-version sort
@@ -110,7 +111,8 @@ struct accmsm_ctx {
     int affine_rounds_override = -1;            // development knob (ACCMSM_AFFINE_ROUNDS), -1 = automatic
     DevBuf<xyzz_t> fold_partial;                // IpaPC::open folded-key materialisation (ipa.cuh)
     DevBuf<uint32_t> fold_flag;
-    int ipa_fold_rounds = 5, ipa_fold_min_log = 14;   // accmsm_set_ipa_fold
+    int ipa_fold_rounds = 5, ipa_fold_min_log = 11;   // accmsm_set_ipa_fold (2^18 -> 2^13 -> 2^8, 2^20 -> 2^15 -> 2^10: profiles/r02v_fold_policy.txt)
+    int fk_small_c = 0;                               // development knob ACCMSM_FK_C: window bits of a materialised key of <= 2^13 points (0 = the rule of registered keys; 10 / 11 / 12 measured slower, profiles/r02w_fk_window.txt)
     // Results that go back to the caller leave the device UN-NORMALISED (XYZZ, 128 B each) and are converted to affine by the
     // host thread that receives them (hostfp.hpp: one inversion for all results of a call)
     xyzz_t *d_out_raw = nullptr;
@@ -220,6 +222,7 @@ int upload_small(accmsm_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, 
     return ACCMSM_OK;
 }
 
+constexpr size_t PRECOMPUTE_COOP_MAX = 1u << 12;    // keys up to this many points build their window table with k_precompute_coop (one group per SM: 0.93 -> 0.65 ms; no gain once two groups share an SM)
 uint32_t pick_window_bits(const accmsm_ctx *ctx, size_t n) {
     if (ctx->window_bits >= 2 && ctx->window_bits <= 16) return (uint32_t)ctx->window_bits;
     uint32_t lg = 0;
@@ -262,9 +265,15 @@ int precompute_table(accmsm_ctx *ctx, Bases &B, int window_bits, affine_t **stor
     } else {
         CU(ctx, cudaMalloc(&table, records * sizeof(affine_t)));
     }
-    uint32_t blocks = (uint32_t)((B.n + 127) / 128);
-    if (B.curve == 0) k_precompute<0><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
-    else k_precompute<1><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+    if (B.n <= PRECOMPUTE_COOP_MAX && !ctx->no_coop_precompute) {      // short key: latency-bound, one cooperative group per 32 bases
+        uint32_t groups = (uint32_t)((B.n + 31) / 32);
+        if (B.curve == 0) k_precompute_coop<0><<<groups, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+        else k_precompute_coop<1><<<groups, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+    } else {
+        uint32_t blocks = (uint32_t)((B.n + 127) / 128);
+        if (B.curve == 0) k_precompute<0><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+        else k_precompute<1><<<blocks, 128, 0, ctx->stream>>>(B.d_xy, (uint32_t)B.n, c, nwin, table);
+    }
     ctx->launches++;
     if (!storage) {      // sessions stay asynchronous: the table is consumed on the same stream
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -952,6 +961,8 @@ int accmsm_init(accmsm_ctx **out, int device) {
     if (const char *e = getenv("ACCMSM_SEG_PCTS")) { for (const char *q = e; *q;) { ctx->seg_pcts.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; } }
     if (const char *e = getenv("ACCMSM_SKIP_H2D")) ctx->skip_h2d = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_TRACE")) ctx->trace = atoi(e) != 0;
+    if (const char *e = getenv("ACCMSM_NO_COOP_PRECOMPUTE")) ctx->no_coop_precompute = atoi(e) != 0;
+    if (const char *e = getenv("ACCMSM_FK_C")) ctx->fk_small_c = atoi(e);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ACCMSM_E_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;

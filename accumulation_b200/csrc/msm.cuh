@@ -1083,6 +1083,53 @@ __global__ void __launch_bounds__(128) k_precompute(const affine_t *__restrict__
     }
 }
 
+// k_precompute_coop: the same table for SHORT keys, where the launch above is bound by the latency of one thread's chain
+// (255 doublings x 9 products + a Fermat inversion, ~0.9 ms whatever the key length): one cooperative group (coop.cuh: four
+// replica warps on the four sub-partitions of an SM) per 32 bases runs every doubling in 3 product phases, the inversion
+// is the binary-GCD one (divergent, but nothing else competes for the SM), and the back-substitution of the windows is
+// dealt round-robin to the four replicas (every replica walks the running inverse, each converts its own windows).
+// Used by the folded keys an IpaPC::open session materialises (ipa_api.inc) and for registered keys up to 2^14 points.
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_precompute_coop(const affine_t *__restrict__ bases, uint32_t n, uint32_t c,
+                                                          uint32_t nwin, affine_t *__restrict__ table) {
+    using Cv = Curve<CURVE, FpCall>;
+    using F = typename Cv::F;
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch;
+    const uint32_t lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    CoopCtx cc{&scratch, role, lane, 1, 0};
+    const uint32_t i = blockIdx.x * 32 + lane;
+    const bool live = i < n;                       // idle lanes of the last group walk a copy of base n - 1 (no stores)
+    affine_t p = load_affine(bases + (live ? i : n - 1));
+    if (live && role == 0) { store_fe(&table[i].x, p.x); store_fe(&table[i].y, p.y); }
+    xyzz_t pts[MAX_PRE_WINDOWS];
+    fe_t pref[MAX_PRE_WINDOWS];
+    xyzz_t cur = Cv::from_affine(p);
+    fe_t run = F::one();
+#pragma unroll 1
+    for (uint32_t w = 1; w < nwin; w++) {
+#pragma unroll 1
+        for (uint32_t b = 0; b < c; b++) cur = Co::dbl(cc, cur);
+        pts[w] = cur;
+        pref[w] = run;
+        run = F::mul(run, cur.zzz);
+    }
+    fe_t inv = F::inv_gcd(run);
+#pragma unroll 1
+    for (uint32_t w = nwin - 1; w >= 1; w--) {
+        if ((w & 3u) == role) {
+            fe_t t = F::mul(inv, pref[w]);            // ZZZ_w^-1
+            fe_t zt = F::mul(pts[w].zz, t);           // ZZ^-1 = (ZZ t)^2 since ZZ^3 = ZZZ^2
+            if (live) {
+                affine_t *dst = table + (size_t)w * n + i;
+                store_fe(&dst->x, F::mul(pts[w].x, F::sqr(zt)));
+                store_fe(&dst->y, F::mul(pts[w].y, t));
+            }
+        }
+        inv = F::mul(inv, pts[w].zzz);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_synth_points: seeded synthetic commitment key for benchmarks / tests: base i is
 // s_i * G with G = (-1, 2) and s_i a 254-bit SplitMix64 value of (seed, global index), so any shard of

@@ -74,7 +74,7 @@ int  accmsm_set_window_bits(accmsm_ctx *ctx, int c);
 /* IpaPC::open sessions: every `rounds` rounds the key folded by the challenges so far is materialised on the device
  * (one shared-scalar batched MSM over the window table) and the session continues on it, while the key the rounds
  * run on still has >= 2^min_log_n points.  rounds = 0: never (every round runs over the registered key).
- * Defaults 5 and 14 (measured, profiles/r01p_ipa_open_fold.txt).  Results are identical either way.  Replaces the per-round key folding
+ * Defaults 5 and 11 (measured, profiles/r02v_fold_policy.txt: 2^18 -> 2^13 -> 2^8 points).  Results are identical either way.  Replaces the per-round key folding
  * `key_l[i] + key_r[i].mul(xi)` of ark-poly-commit ipa_pc `open` (reached from src/ipa_pc_as/mod.rs:454-462). */
 int  accmsm_set_ipa_fold(accmsm_ctx *ctx, int rounds, int min_log_n);
 /* number of this library's kernels launched by ctx so far (bench.py reports it as gpu_launches) */
