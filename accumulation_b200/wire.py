@@ -17,7 +17,7 @@ Host-side formats only -- byte shuffling, no field arithmetic on the hot path:
 
 The large direction of the key format -- decompressing n x 33 B into an HBM-resident key -- runs on the device:
 `Context.register_bases_compressed` (csrc/wire.cuh).  Everything here follows the published sources of the pinned
-dependency versions as recalled offline; `tools/make_ref_fixtures.rs` is the recipe that produces fixtures from a real
+dependency versions as recalled offline; `tools/ref_fixtures/ (cargo run --release)` is the recipe that produces fixtures from a real
 arkworks build, and `tests/test_ref_fixtures.py` replays them when they are present.  Until such fixtures exist the
 parity of this module with arkworks is UNPINNED (the ChaCha20 core alone is pinned, by RFC 8439's block test vector).
 """

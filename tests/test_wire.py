@@ -3,7 +3,7 @@
 CPU suite: the ChaCha20 core against RFC 8439's block test vector, the BlockRng word pairing, ark-ff's UniformRand rule,
 round trips of every serialised type, rejection of invalid encodings.  GPU suite: a compressed commitment key is
 decompressed on the device (Tonelli-Shanks per point) bit-exactly, also through a device group, and keys serialise back.
-Parity with arkworks itself stays unpinned until fixtures from tools/make_ref_fixtures.rs exist (tests/test_ref_fixtures.py)."""
+Parity with arkworks itself stays unpinned until fixtures from tools/ref_fixtures/ (cargo run --release) exist (tests/test_ref_fixtures.py)."""
 import numpy as np
 import pytest
 

@@ -10,7 +10,7 @@ import accumulation_b200 as ab
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--min", type=int, default=12); ap.add_argument("--max", type=int, default=24)
-ap.add_argument("--cpu-max", type=int, default=22); ap.add_argument("--curves", default="0,1")
+ap.add_argument("--cpu-max", type=int, default=24); ap.add_argument("--curves", default="0,1")
 args = ap.parse_args()
 ctx = ab.Context(0)
 for curve in [int(c) for c in args.curves.split(",")]:
@@ -32,6 +32,15 @@ for curve in [int(c) for c in args.curves.split(",")]:
         rec = {"curve": "pallas" if curve == 0 else "vesta", "log_n": k, "gpu_ms": round(min(dev), 4), "gpu_mpts": round(n / min(dev) / 1e3, 2),
                "e2e_ms": round(min(e2e), 4), "e2e_mpts": round(n / min(e2e) / 1e3, 2), "register_ms": round((t_pre) * 1e3, 2),
                "stages_ms": {a: round(b, 4) for a, b in st.items() if b > 0.0005}}
+        # size-independent check at every size: MSM(bases[0, n)) == MSM(bases[0, n/2)) + MSM(bases[n/2, n)), the halves through the
+        # offset / n arguments of the same entry point and the final addition on the CPU (a two-term MSM with scalars 1, 1)
+        from oracle import cref
+        h1 = ctx.msm_dev(key, d.data_ptr(), n // 2, montgomery=False, offset=0)
+        h2 = ctx.msm_dev(key, d.data_ptr() + (n // 2) * 32, n - n // 2, montgomery=False, offset=n // 2)
+        parts = [p for p in (h1, h2) if not p[1]]
+        one = np.array([[1, 0, 0, 0]] * len(parts), dtype=np.uint64)
+        ssum = cref.msm_ark(curve, np.array([p[0] for p in parts]), one) if parts else None
+        rec["split_sum_equal"] = bool(ssum is not None and ssum[1] == got[1] and np.array_equal(ssum[0], got[0]) and np.array_equal(got2[0], got[0]))
         if k <= args.cpu_max:
             from oracle import cref
             pts = ctx.download_bases(key)

@@ -23,6 +23,28 @@ for curve in (0, 1):
         ctx.ipa_final_key(key, scal(11))
     pts = ctx.download_bases(key, 0, 64)
     ctx.msm_oneshot(curve, pts, scal(64), montgomery=False)
+    ctx.msm_oneshot_batch(curve, ctx.download_bases(key, 0, 11 * 43).reshape(11, 43, 8), scal(11 * 43).reshape(11, 43, 4), montgomery=False)   # two passes of <= 8 jobs
+    # wire formats: compressed ark-serialize image -> decompression kernel (Tonelli-Shanks) -> the same key
+    blob = ctx.serialize_bases(key, 0, 200)
+    k2 = ctx.register_bases_compressed(curve, blob); assert (ctx.download_bases(k2) == ctx.download_bases(key, 0, 200)).all(); k2.release()
+    # long pass: the radix sort staged through shared memory (sort.cuh; >= 2^17 (bucket, point) pairs) on a table key
+    big = ctx.register_synthetic_bases(curve, 6, 20000); big.precompute(10)
+    r1 = ctx.msm(big, scal(20000), montgomery=False)
+    ctx.msm(big, np.repeat(scal(1), 20000, axis=0), montgomery=False)       # constant vector: the skew gate hands over to the counting sort
+    import torch
+    d_part = torch.zeros(16, dtype=torch.int64, device="cuda")
+    ctx.msm_partial(big, scal(20000), d_part.data_ptr(), montgomery=False)
+    ctx.combine_partials_dev(curve, d_part.data_ptr(), 1)
+    big.release()
+    if curve == 0 and os.environ.get("SANITIZE_LARGE"):
+        # host-scalar MSM of >= 16 MiB: two point segments, the second uploaded behind the accumulation of the first (k_accumulate `into` mode)
+        huge = ctx.register_synthetic_bases(0, 9, 1 << 19); huge.precompute()
+        sc = scal(1 << 19)
+        got = ctx.msm(huge, sc, montgomery=False)
+        d = torch.from_numpy(sc.view(np.int64)).cuda()
+        ref = ctx.msm_dev(huge, d.data_ptr(), 1 << 19, montgomery=False)
+        assert got[1] == ref[1] and (got[0] == ref[0]).all()
+        huge.release()
     a, b = scal(n), scal(n)
     ctx.hadamard(sf, a, b); ctx.scale(sf, a, b[0]); ctx.lincomb(sf, [a, b[:100]], scal(2), a[:50])
     ctx.tvecs(sf, [a, b], [b, a], scal(3), n, a, b)
