@@ -97,7 +97,7 @@ struct accmsm_ctx {
     DevBuf<uint2> sort_pairs;                                   // sort.cuh: (key low bits, entry) pairs in partition order
     DevBuf<uint32_t> sort_tile_count, sort_part_count, sort_part_offs;
     int segments_override = 0;                                  // development knob (ACCMSM_SEGMENTS): point segments of a large host-scalar MSM (1 = no pipelining)
-    int seg0_pct = 12;                                          // share of the first of two segments (ACCMSM_SEG0_PCT)
+    int seg0_pct = 25;                                          // share of the first of two segments (ACCMSM_SEG0_PCT)
     std::vector<int> seg_pcts;                                  // development knob (ACCMSM_SEG_PCTS="12,60"): cumulative segment boundaries in percent
     int seg_calls = 0;
     bool no_coop_precompute = false;                            // development knob (ACCMSM_NO_COOP_PRECOMPUTE)
@@ -124,6 +124,13 @@ struct accmsm_ctx {
     bool stage_busy = false;
     std::vector<cudaEvent_t> chunk_events;   // download() / chunked upload: one per 4 MiB chunk
     cudaStream_t copy_stream = nullptr;      // chunked upload of large scalar vectors (msm_host_scalars)
+    // Side stream for launches that are off the critical path of a pass: the gated fallback sort of a long pass (its kernels
+    // return at once unless the radix sort stood down) runs beside the radix sort's write / bucket passes, and the fix-up
+    // of a point segment beside the sort of the next one.  aux_fork orders it after the launching stream, aux_join back.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    bool aux_dirty = false;                  // work enqueued on aux_stream that the launching stream has not waited for yet
+    bool no_aux = false;                     // development knob (ACCMSM_NO_AUX): everything on the launching stream
     cudaEvent_t ev[ST_COUNT + 1];
     bool ev_valid[ST_COUNT + 1];
     float timings[ST_COUNT];
@@ -194,6 +201,31 @@ void trace_point(accmsm_ctx *ctx, cudaStream_t st, const std::string &label) {
     if (!ctx->trace) return;
     cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st);
     ctx->trace_ev.push_back({label, ev});
+}
+
+// side stream (see accmsm_ctx::aux_stream): aux_begin makes it wait for everything enqueued on `st` so far and returns it
+// (or `st` itself when the side stream is unavailable / switched off); aux_sync makes `st` wait for everything enqueued on it
+cudaStream_t aux_begin(accmsm_ctx *ctx, cudaStream_t st) {
+    if (ctx->no_aux) return st;
+    if (!ctx->aux_stream) {
+        if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError(); ctx->no_aux = true; return st;
+        }
+    }
+    if (cudaEventRecord(ctx->aux_fork, st) != cudaSuccess || cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0) != cudaSuccess) {
+        (void)cudaGetLastError(); return st;
+    }
+    ctx->aux_dirty = true;
+    return ctx->aux_stream;
+}
+int aux_sync(accmsm_ctx *ctx, cudaStream_t st) {
+    if (!ctx->aux_dirty) return ACCMSM_OK;
+    CU(ctx, cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+    CU(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
+    ctx->aux_dirty = false;
+    return ACCMSM_OK;
 }
 
 // workspace ordering across streams (see accmsm_ctx::ws_done)
@@ -369,7 +401,7 @@ template <class Src> bool sort_opt_in() {
 // n_for_c: the length that picks the window size of a plain key (all segments of one MSM must agree on it).
 template <int CURVE, class Src>
 int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t n, size_t n_for_c, const Src &src, bool into,
-                   cudaStream_t st, MsmShape *sh_out) {
+                   cudaStream_t st, MsmShape *sh_out, bool fixup_aside = false) {
     MsmShape sh = make_shape(ctx, B, jobs, n, n_for_c);
     *sh_out = sh;
     const bool tabled = sh.ent_stride != 0;
@@ -387,6 +419,7 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
     // inputs.  Short passes: the counting sort alone (3 launches; with a few thousand pairs nothing is bandwidth-bound).
     const bool radix = ctx->sort_lb_override >= 0 && n_entries >= (size_t(1) << 17) && sh.nkeys >= 1024u;
     SortGate fallback{nullptr, 0};
+    cudaStream_t fb = st;                // stream of the first-version sort: `st`, or the side stream behind a radix sort
     if (radix) {
         SortPlan pl;
         pl.lb = ctx->sort_lb_override > 0 ? (uint32_t)ctx->sort_lb_override : 9;      // measured: 9 beats 10 and 11 at 2^19 buckets
@@ -420,6 +453,8 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
         k_sort_tile_scan<<<(pl.nparts + TS_PARTS - 1) / TS_PARTS, TS_PARTS * TS_SEGS, 0, st>>>(tile_count, pl.ntiles, pl.nparts, ctx->sort_part_count.p, max_part);
         ctx->launches += 2;
         { int src2 = launch_scan(ctx, ctx->sort_part_count.p, pl.nparts, ctx->sort_part_offs.p, nullptr, st); if (src2) return src2; }
+        // the gate word is final: the fallback chain below goes to the side stream, next to the write / bucket passes
+        fb = aux_begin(ctx, st);
         mark(ctx, ST_SCATTER, st);
         trace_point(ctx, st, "  counted + scanned");
         k_sort_tiles<Src, true><<<pl.ntiles, SORT_THREADS, smem1, st>>>(src, sh, B.d_inf, pl, 0u, pl.tiles_per_job, tile_count, tile_hist, ctx->sort_part_offs.p, ctx->sort_pairs.p, gate);
@@ -433,16 +468,17 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
         CU(ctx, ctx->digits.ensure(n_entries));
         CU(ctx, ctx->cursor.ensure(sh.nkeys));
         if (!radix) mark(ctx, ST_DIGITS, st);
-        CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), st));
+        CU(ctx, cudaMemsetAsync(ctx->hist.p, 0, sh.nkeys * sizeof(uint32_t), fb));
         // behind the gate: a small grid (grid-stride loops), so standing down costs next to nothing
         dim3 blocks(radix ? std::min<uint32_t>((sh.n + 255) / 256, (uint32_t)ctx->sm_count * 8) : (sh.n + 255) / 256, sh.njobs);
-        k_digits<Src><<<blocks, 256, 0, st>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p, 0u, sh.n, fallback);
+        k_digits<Src><<<blocks, 256, 0, fb>>>(src, sh, B.d_inf, ctx->digits.p, ctx->hist.p, 0u, sh.n, fallback);
         if (!radix) mark(ctx, ST_SCAN, st);
-        { int src2 = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p, st, fallback); if (src2) return src2; }
+        { int src2 = launch_scan(ctx, ctx->hist.p, sh.nkeys, ctx->offsets.p, ctx->cursor.p, fb, fallback); if (src2) return src2; }
         if (!radix) mark(ctx, ST_SCATTER, st);
-        k_scatter<<<blocks, 256, 0, st>>>(sh, ctx->digits.p, ctx->cursor.p, ctx->entries.p, fallback);
+        k_scatter<<<blocks, 256, 0, fb>>>(sh, ctx->digits.p, ctx->cursor.p, ctx->entries.p, fallback);
         ctx->launches += 2;
     }
+    { int arc = aux_sync(ctx, st); if (arc) return arc; }      // fallback chain (and an earlier segment's fix-up) before the buckets are touched
     mark(ctx, ST_ACCUMULATE, st);
     trace_point(ctx, st, "  gated fallback sort passed");
     if (!into && sh.nkeys <= ACC_WARP_MAX_KEYS && n_entries <= ACC_WARP_MAX_ENTRIES) {
@@ -503,7 +539,10 @@ int msm_accumulate(accmsm_ctx *ctx, const Bases &B, const MsmJobs &jobs, size_t 
         // accmsm_init (acc_ctas_per_sm) so that they fit; a part with more SMs than that cap assumes must fail loudly, not overflow
         if (ns > (uint32_t)(FIX_THREADS * FIX_PER_T)) return fail_arg(ctx, "msm: accumulate grid exceeds the fix-up kernel's slots");
         size_t smem2 = ns * (sizeof(xyzz_t) + sizeof(uint32_t));
-        k_fixup<CURVE><<<1, FIX_THREADS, smem2, st>>>(ctx->cta_ids.p, ctx->cta_parts.p, ns, ctx->buckets.p);
+        // fixup_aside: more point segments follow (msm_host_scalars) -- the fix-up runs beside the sort of the next segment
+        // and is waited for before that segment's accumulation touches the buckets (aux_sync above)
+        cudaStream_t fx = fixup_aside ? aux_begin(ctx, st) : st;
+        k_fixup<CURVE><<<1, FIX_THREADS, smem2, fx>>>(ctx->cta_ids.p, ctx->cta_parts.p, ns, ctx->buckets.p);
         ctx->launches += 2;
     }
     return ACCMSM_OK;
@@ -518,6 +557,7 @@ int msm_reduce(accmsm_ctx *ctx, const MsmShape &sh, bool use_offsets, const xyzz
     ctx->out_curve = CURVE;
     const uint32_t nsets = sh.njobs * sh.sets_per_job;          // bucket sets to reduce
     const uint32_t *offs = use_offsets ? ctx->offsets.p : nullptr;
+    { int arc = aux_sync(ctx, st); if (arc) return arc; }
     mark(ctx, ST_REDUCE, st);
     const xyzz_t *window_sums = nullptr;
     {
@@ -748,12 +788,15 @@ const Bases *find_bases(accmsm_ctx *ctx, uint64_t handle) {
 // normalisation.  d_partial (nullable): where the un-normalised sum goes (DEVICE memory, possibly a peer GPU's);
 // normalise: the result goes to ctx->d_out_raw (XYZZ; fetch_affine converts it on the host).  The caller fetches / synchronises.
 //
-// Large vectors (>= 16 MiB) hide the PCIe transfer behind the arithmetic: the points are cut into two segments of about
-// 1/8 and 7/8 of the vector (measured best of 12 / 25 / 37 %: profiles/r02i_*; the accumulation of a segment takes ~4x as long as the upload of the same number of
-// scalars), the upload runs on a copy stream in 4 MiB chunks, and the second segment travels while the first one is sorted
-// and accumulated; both segments add into ONE zero-initialised bucket set (k_accumulate `into` mode: no extra
-// additions), then one reduction.  Exposed transfer: the first fifth.  Pageable sources are staged chunk by chunk into
-// page-locked memory by 4 threads on the way.
+// Large vectors (>= 16 MiB) hide the PCIe transfer behind the arithmetic: the points are cut into two segments of 1/4 and
+// 3/4 of the vector, the upload runs on a copy stream in 4 MiB chunks, and the second segment travels while the first one is
+// sorted and accumulated; both segments add into ONE zero-initialised bucket set (k_accumulate `into` mode: no extra
+// additions), then one reduction; the fix-up of the first segment runs on the side stream beside the sort of the second.
+// The split balances "work on segment 0" against "upload of the rest" (0.15 + 2.3 f ms against 0.63 (1 - f) ms on a PCIe 5
+// x16 link: f ~ 0.17; 12 % leaves the GPU waiting for data, 37 % exposes more of the first upload -- profiles/r02i_*,
+// r02z_e2e_aux.txt; slower uploads, e.g. eight GPUs sharing one host, favour the larger first segment).  Every segment
+// pays ~0.15 ms of fixed cost (sort launches, slice merge), so two segments beat three.  Pageable sources are staged chunk
+// by chunk into page-locked memory by 4 threads on the way.
 int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, const uint64_t *scalars, int mont,
                      const xyzz_t *d_extra, uint32_t n_extra, xyzz_t *d_partial, bool normalise) {
     cudaStream_t st = ctx->stream;
@@ -833,9 +876,9 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
         const uint8_t *ptr = ctx->scalars.p + e0 * 32;
         int rc;
         if (B.curve == 0) { MemScalars<1> ms; ms.montgomery = mont; for (uint32_t j = 0; j < MAX_JOBS; j++) ms.ptr[j] = j ? nullptr : ptr;
-                            rc = msm_accumulate<0>(ctx, B, MsmJobs(offset + e0), e1 - e0, n, ms, true, st, &sh); }
+                            rc = msm_accumulate<0>(ctx, B, MsmJobs(offset + e0), e1 - e0, n, ms, true, st, &sh, c1 < nchunks); }
         else { MemScalars<0> ms; ms.montgomery = mont; for (uint32_t j = 0; j < MAX_JOBS; j++) ms.ptr[j] = j ? nullptr : ptr;
-               rc = msm_accumulate<1>(ctx, B, MsmJobs(offset + e0), e1 - e0, n, ms, true, st, &sh); }
+               rc = msm_accumulate<1>(ctx, B, MsmJobs(offset + e0), e1 - e0, n, ms, true, st, &sh, c1 < nchunks); }
         if (rc) return rc;
         tr("seg" + std::to_string(g) + " accumulated");
         c0 = c1;
@@ -961,6 +1004,7 @@ int accmsm_init(accmsm_ctx **out, int device) {
     if (const char *e = getenv("ACCMSM_SEG_PCTS")) { for (const char *q = e; *q;) { ctx->seg_pcts.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; } }
     if (const char *e = getenv("ACCMSM_SKIP_H2D")) ctx->skip_h2d = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_TRACE")) ctx->trace = atoi(e) != 0;
+    if (const char *e = getenv("ACCMSM_NO_AUX")) ctx->no_aux = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_NO_COOP_PRECOMPUTE")) ctx->no_coop_precompute = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_FK_C")) ctx->fk_small_c = atoi(e);
     cudaDeviceProp prop;
@@ -1042,6 +1086,9 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     if (ctx->h_args) cudaFreeHost(ctx->h_args);
     for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
