@@ -274,6 +274,16 @@ impl<'k> IpaOpenSession<'k> {
     pub fn fold<S: Fp256Parameters>(&mut self, xi: Fp256<S>, xi_inv: Fp256<S>) -> Result<()> {
         self.key.ctx.check(unsafe { ffi::accmsm_ipa_open_fold(self.key.ctx.raw, self.id, (xi.0).0.as_ptr(), (xi_inv.0).0.as_ptr()) })
     }
+    /// One call per round of the opening loop: fold with the challenge squeezed from the previous `(l, r)` (its inverse is
+    /// computed inside the library, on the host, like upstream's `round_challenge.inverse()`) and run the next round.
+    /// `None` when that fold was the last one: call `finish` next.
+    pub fn fold_round<P: GpuCurve + GpuBase, S: Fp256Parameters>(&mut self, xi: Fp256<S>) -> Result<Option<(GroupAffine<P>, GroupAffine<P>)>> {
+        let (mut l, mut r, mut li, mut ri, mut done) = ([0u64; 8], [0u64; 8], 0u8, 0u8, 0 as c_int);
+        self.key.ctx.check(unsafe {
+            ffi::accmsm_ipa_open_fold_round(self.key.ctx.raw, self.id, (xi.0).0.as_ptr(), l.as_mut_ptr(), &mut li, r.as_mut_ptr(), &mut ri, &mut done)
+        })?;
+        Ok(if done != 0 { None } else { Some((affine_from::<P>(&l, li), affine_from::<P>(&r, ri))) })
+    }
     pub fn finish<P: GpuCurve + GpuBase, S: Fp256Parameters>(mut self) -> Result<(GroupAffine<P>, Fp256<S>)> {
         let (mut fk, mut c) = ([0u64; 8], [0u64; 4]);
         self.finished = true;
@@ -288,6 +298,25 @@ impl<'k> Drop for IpaOpenSession<'k> {
             unsafe { ffi::accmsm_ipa_open_finish(self.key.ctx.raw, self.id, fk.as_mut_ptr(), c.as_mut_ptr()) };   // releases the session
         }
     }
+}
+
+/// `VariableBaseMSM::multi_scalar_mul(&bases, &scalars).into_affine()` for `m` independent MSMs of equal length over their own,
+/// unregistered bases in shared passes of the pipeline: the succinct-check group equations of all inputs and accumulators of
+/// one ipa-pc-as prove / verify (src/ipa_pc_as/mod.rs:198-205 inside the loops at :262-270 and :625-640).
+pub fn msm_oneshot_batch<P: GpuCurve + GpuBase>(ctx: &Context, bases: &[&[GroupAffine<P>]], scalars: &[&[BigInteger256]]) -> Result<Vec<GroupAffine<P>>> {
+    let m = bases.len().min(scalars.len());
+    let n = (0..m).map(|j| bases[j].len().min(scalars[j].len())).min().unwrap_or(0);
+    let (mut xy, mut inf, mut sc) = (Vec::<u64>::with_capacity(m * n * 8), Vec::<u8>::with_capacity(m * n), Vec::<u64>::with_capacity(m * n * 4));
+    for j in 0..m {
+        for i in 0..n {
+            let g = &bases[j][i];
+            xy.extend_from_slice(&P::base_limbs(&g.x)); xy.extend_from_slice(&P::base_limbs(&g.y)); inf.push(g.infinity as u8);
+            sc.extend_from_slice(&scalars[j][i].0);
+        }
+    }
+    let (mut out, mut oinf) = (vec![0u64; 8 * m], vec![0u8; m]);
+    ctx.check(unsafe { ffi::accmsm_msm_oneshot_batch(ctx.raw, P::CURVE_ID, xy.as_ptr(), inf.as_ptr(), sc.as_ptr(), 0, n, m, out.as_mut_ptr(), oinf.as_mut_ptr()) })?;
+    Ok((0..m).map(|j| { let mut a = [0u64; 8]; a.copy_from_slice(&out[8 * j..8 * j + 8]); affine_from::<P>(&a, oinf[j]) }).collect())
 }
 
 /// Field-vector kernels of the in-tree loops (src/hp_as/mod.rs:278-285,482-512; src/ipa_pc_as/mod.rs:400).
