@@ -104,7 +104,8 @@ struct accmsm_ctx {
     bool skip_h2d = false, trace = false;                       // development knobs (ACCMSM_SKIP_H2D: timing experiments only -- reuses the scalars of the previous call; ACCMSM_TRACE)
     std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
     int sort_lb_override = 0;                                   // development knob (ACCMSM_SORT_LB), 0 = automatic; -1 = first-version sort
-    DevBuf<uint8_t> oneshot_inf;
+    DevBuf<uint8_t> oneshot_inf, ipa_tabs;      // ipa_tabs: half tables of h(X)'s coefficients (ipa_half_tables)
+    bool no_ipa_tabs = false;                   // development knob (ACCMSM_NO_IPA_TABS)
     DevBuf<affine_t> oneshot_xy, pair_pts[2];   // pair_pts / pair_off: ping-pong lists of the batch-affine rounds
     DevBuf<uint32_t> pair_off[2];
     DevBuf<uint8_t> pair_pref, pair_kinds, pair_tfac, pair_ctot, pair_cfac;
@@ -1005,6 +1006,7 @@ int accmsm_init(accmsm_ctx **out, int device) {
     if (const char *e = getenv("ACCMSM_SKIP_H2D")) ctx->skip_h2d = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_NO_AUX")) ctx->no_aux = atoi(e) != 0;
+    if (const char *e = getenv("ACCMSM_NO_IPA_TABS")) ctx->no_ipa_tabs = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_NO_COOP_PRECOMPUTE")) ctx->no_coop_precompute = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_FK_C")) ctx->fk_small_c = atoi(e);
     cudaDeviceProp prop;
@@ -1071,7 +1073,7 @@ void accmsm_destroy(accmsm_ctx *ctx) {
     for (auto &b : ctx->vec_cache) cudaFree(b.first);
     ctx->digits.release(); ctx->hist.release(); ctx->offsets.release(); ctx->cursor.release(); ctx->entries.release();
     ctx->cta_ids.release(); ctx->tile_sums.release(); ctx->tile_offs.release(); ctx->buckets.release(); ctx->cta_parts.release(); ctx->partial.release();
-    ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release(); ctx->oneshot_inf.release();
+    ctx->scalars.release(); ctx->misc.release(); ctx->oneshot_xy.release(); ctx->oneshot_inf.release(); ctx->ipa_tabs.release();
     ctx->sort_pairs.release(); ctx->sort_tile_count.release(); ctx->sort_part_count.release(); ctx->sort_part_offs.release();
     for (int i = 0; i < 2; i++) { ctx->pair_pts[i].release(); ctx->pair_off[i].release(); }
     ctx->fold_partial.release(); ctx->fold_flag.release();
@@ -1453,13 +1455,32 @@ int accmsm_combine_partials_batch_dev(accmsm_ctx *ctx, int curve, const void *d_
     return fetch_points(ctx, curve, ctx->d_out_raw, m, out_xy, out_inf, st);
 }
 
+// Half tables of h(X)'s coefficients for IpaScalars (msm.cuh), built on `st` into ctx->ipa_tabs: worth it once the MSM has
+// more coefficients than the tables have entries.  *lo / *hi stay NULL otherwise (the per-bit loop is used).
+static int ipa_half_tables(accmsm_ctx *ctx, int sfield, const uint8_t *d_challenges, int k, size_t n, cudaStream_t st,
+                           const uint8_t **lo, const uint8_t **hi) {
+    *lo = *hi = nullptr;
+    if (k < 8 || k > 30 || ctx->no_ipa_tabs) return ACCMSM_OK;
+    const uint32_t kl = (uint32_t)k / 2u, entries = (1u << kl) + (1u << ((uint32_t)k - kl));
+    if (n < 4 * (size_t)entries) return ACCMSM_OK;
+    CU(ctx, ctx->ipa_tabs.ensure((size_t)entries * 32));
+    if (sfield == 0) k_ipa_half_tables<0><<<(entries + 255) / 256, 256, 0, st>>>(d_challenges, k, ctx->ipa_tabs.p);
+    else k_ipa_half_tables<1><<<(entries + 255) / 256, 256, 0, st>>>(d_challenges, k, ctx->ipa_tabs.p);
+    ctx->launches++;
+    *lo = ctx->ipa_tabs.p;
+    *hi = ctx->ipa_tabs.p + ((size_t)1 << kl) * 32;
+    return ACCMSM_OK;
+}
+
 static int ipa_run(accmsm_ctx *ctx, const Bases &B, const uint64_t *challenges_mont, int k, size_t coeff_offset, size_t n,
                    xyzz_t *d_partial, bool normalise, cudaStream_t st) {
     CU(ctx, ctx->misc.ensure(64 * 32));
     { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
     if (k) { int urc = upload_small(ctx, ctx->misc.p, challenges_mont, (size_t)k * 32, st); if (urc) return urc; }
-    if (B.curve == 0) { IpaScalars<1> src{ctx->misc.p, k, (uint32_t)coeff_offset}; return run_msm<0>(ctx, B, MsmJobs(0), n, src, nullptr, 0, d_partial, normalise, st); }
-    IpaScalars<0> src{ctx->misc.p, k, (uint32_t)coeff_offset};
+    const uint8_t *lo = nullptr, *hi = nullptr;
+    { int trc = ipa_half_tables(ctx, B.curve == 0 ? 1 : 0, ctx->misc.p, k, n, st, &lo, &hi); if (trc) return trc; }
+    if (B.curve == 0) { IpaScalars<1> src{ctx->misc.p, k, (uint32_t)coeff_offset, lo, hi}; return run_msm<0>(ctx, B, MsmJobs(0), n, src, nullptr, 0, d_partial, normalise, st); }
+    IpaScalars<0> src{ctx->misc.p, k, (uint32_t)coeff_offset, lo, hi};
     return run_msm<1>(ctx, B, MsmJobs(0), n, src, nullptr, 0, d_partial, normalise, st);
 }
 

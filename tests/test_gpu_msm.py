@@ -517,6 +517,35 @@ def test_chunked_upload_overlapping_the_digit_kernel(ctx, pinned):
     key.release()
 
 
+@pytest.mark.parametrize("kind", ["constant", "a_a_a_0", "two_values", "trunc128"])
+def test_pipelined_upload_with_degenerate_scalar_vectors(ctx, kind):
+    """The two-segment pipeline of a large host-scalar MSM (both segments add into one bucket set; fix-up and the gated
+    fallback sort on the side stream) on the reference's degenerate scalar vectors: a constant vector (src/hp_as/mod.rs:991)
+    and (a, ..., a, 0) (examples/scaling-nark.rs:48-52) close the skew gate of the radix sort in BOTH segments, so the
+    counting sort feeds the `into` accumulation with one hot bucket per window; two values and 128-bit challenges likewise
+    stress single partitions.  Bit-exact with the oracle and with the device-resident (unsegmented) MSM."""
+    import torch
+    n = (1 << 19) + 333
+    key = ctx.register_synthetic_bases(0, 79, n)
+    key.precompute()
+    rnd = cref.gen_scalars(cref.FQ, 80, n, False)
+    if kind == "constant":
+        sc = np.repeat(rnd[:1], n, axis=0)
+    elif kind == "a_a_a_0":
+        sc = np.repeat(rnd[:1], n, axis=0); sc[-1] = 0
+    elif kind == "two_values":
+        sc = np.where((np.arange(n) % 3 == 0)[:, None], rnd[0], rnd[1])
+    else:
+        sc = rnd.copy(); sc[:, 2:] = 0
+    sc = np.ascontiguousarray(sc, dtype=np.uint64)
+    got = ctx.msm(key, sc, montgomery=False)
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    dev = ctx.msm_dev(key, d_sc.data_ptr(), n, montgomery=False)
+    assert same_point(got, dev)
+    assert same_point(got, cref.msm_ark(0, ctx.download_bases(key), sc))
+    key.release()
+
+
 @pytest.mark.parametrize("curve", [0, 1])
 @pytest.mark.parametrize("precompute", [False, True])
 def test_reduction_tree_meets_equal_and_opposite_points(ctx, curve, precompute):
