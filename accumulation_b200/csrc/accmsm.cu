@@ -99,13 +99,13 @@ struct accmsm_ctx {
     int segments_override = 0;                                  // development knob (ACCMSM_SEGMENTS): point segments of a large host-scalar MSM (1 = no pipelining)
     int seg0_pct = 25;                                          // share of the first of two segments (ACCMSM_SEG0_PCT)
     std::vector<int> seg_pcts;                                  // development knob (ACCMSM_SEG_PCTS="12,60"): cumulative segment boundaries in percent
-    int seg_calls = 0;
     bool no_coop_precompute = false;                            // development knob (ACCMSM_NO_COOP_PRECOMPUTE)
-    bool skip_h2d = false, trace = false;                       // development knobs (ACCMSM_SKIP_H2D: timing experiments only -- reuses the scalars of the previous call; ACCMSM_TRACE)
+    bool trace = false;                                         // development knob ACCMSM_TRACE: timeline of the segments of a pipelined host-scalar MSM on stderr
     std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
     int sort_lb_override = 0;                                   // development knob (ACCMSM_SORT_LB), 0 = automatic; -1 = first-version sort
     DevBuf<uint8_t> oneshot_inf, ipa_tabs;      // ipa_tabs: half tables of h(X)'s coefficients (ipa_half_tables)
     bool no_ipa_tabs = false;                   // development knob (ACCMSM_NO_IPA_TABS)
+    bool no_coop_finish = false;                // development knob (ACCMSM_NO_COOP_FINISH)
     DevBuf<affine_t> oneshot_xy, pair_pts[2];   // pair_pts / pair_off: ping-pong lists of the batch-affine rounds
     DevBuf<uint32_t> pair_off[2];
     DevBuf<uint8_t> pair_pref, pair_kinds, pair_tfac, pair_ctot, pair_cfac;
@@ -628,7 +628,10 @@ int msm_reduce(accmsm_ctx *ctx, const MsmShape &sh, bool use_offsets, const xyzz
         window_sums = sums;
     }
     mark(ctx, ST_FINISH, st);
-    k_finish<CURVE><<<sh.njobs, 32, 0, st>>>(window_sums, sh.sets_per_job, sh.c, d_extra, n_extra, d_partial, normalise ? d_out_raw : nullptr);
+    if (sh.sets_per_job > 1 && !ctx->no_coop_finish)      // plain key: Horner over the windows by a cooperative group
+        k_finish_coop<CURVE><<<sh.njobs, 128, 0, st>>>(window_sums, sh.sets_per_job, sh.c, d_extra, n_extra, d_partial, normalise ? d_out_raw : nullptr);
+    else
+        k_finish<CURVE><<<sh.njobs, 32, 0, st>>>(window_sums, sh.sets_per_job, sh.c, d_extra, n_extra, d_partial, normalise ? d_out_raw : nullptr);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     return ws_release(ctx, st);
@@ -847,7 +850,7 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
             }
             from = stage + off;
         }
-        if (!ctx->skip_h2d || ctx->seg_calls == 0) CU(ctx, cudaMemcpyAsync(ctx->scalars.p + off, from, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(ctx, cudaMemcpyAsync(ctx->scalars.p + off, from, len, cudaMemcpyHostToDevice, ctx->copy_stream));
         CU(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
         return ACCMSM_OK;
     };
@@ -885,7 +888,6 @@ int msm_host_scalars(accmsm_ctx *ctx, const Bases &B, size_t offset, size_t n, c
         c0 = c1;
     }
     if (pageable) { CU(ctx, cudaEventRecord(ctx->stage_done, ctx->copy_stream)); ctx->stage_busy = true; }
-    ctx->seg_calls++;
     const int rrc = B.curve == 0 ? msm_reduce<0>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr)
                                  : msm_reduce<1>(ctx, sh, false, d_extra, n_extra, d_partial, normalise, st, nullptr);
     tr("reduced");
@@ -1003,10 +1005,10 @@ int accmsm_init(accmsm_ctx **out, int device) {
     if (const char *e = getenv("ACCMSM_SEGMENTS")) ctx->segments_override = atoi(e);
     if (const char *e = getenv("ACCMSM_SEG0_PCT")) ctx->seg0_pct = std::min(90, std::max(1, atoi(e)));
     if (const char *e = getenv("ACCMSM_SEG_PCTS")) { for (const char *q = e; *q;) { ctx->seg_pcts.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; } }
-    if (const char *e = getenv("ACCMSM_SKIP_H2D")) ctx->skip_h2d = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_NO_AUX")) ctx->no_aux = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_NO_IPA_TABS")) ctx->no_ipa_tabs = atoi(e) != 0;
+    if (const char *e = getenv("ACCMSM_NO_COOP_FINISH")) ctx->no_coop_finish = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_NO_COOP_PRECOMPUTE")) ctx->no_coop_precompute = atoi(e) != 0;
     if (const char *e = getenv("ACCMSM_FK_C")) ctx->fk_small_c = atoi(e);
     cudaDeviceProp prop;

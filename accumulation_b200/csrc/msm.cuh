@@ -1053,6 +1053,37 @@ __global__ void k_finish(const xyzz_t *__restrict__ window_sums, uint32_t nwin, 
     if (out_raw) store_xyzz(out_raw + job, acc);
 }
 
+// k_finish for PLAIN keys (no window table): the Horner over the windows is ~256 dependent doublings -- 0.8 ms on one thread,
+// the whole latency of a one-shot MSM (succinct-check equations, short commitment combinations).  One cooperative group
+// (coop.cuh) per job runs every doubling in 3 product phases and every addition in 4; all lanes carry the same point.
+template <int CURVE>
+__global__ void __launch_bounds__(128) k_finish_coop(const xyzz_t *__restrict__ window_sums, uint32_t nwin, uint32_t c,
+                                                      const xyzz_t *__restrict__ extra, uint32_t n_extra,
+                                                      xyzz_t *__restrict__ out_partial, xyzz_t *__restrict__ out_raw) {
+    using Cv = Curve<CURVE, FpCall>;
+    using Co = Coop<CURVE>;
+    __shared__ CoopScratch scratch;
+    CoopCtx cc{&scratch, threadIdx.x >> 5, threadIdx.x & 31, 1, 0};
+    const uint32_t job = blockIdx.x;
+    window_sums += (size_t)job * nwin;
+    xyzz_t acc = Cv::identity();
+#pragma unroll 1
+    for (int w = (int)nwin - 1; w >= 0; w--) {
+        if (!Cv::is_identity(acc)) {                 // uniform across the group: every lane holds the same point
+#pragma unroll 1
+            for (uint32_t b = 0; b < c; b++) acc = Co::dbl(cc, acc);
+        }
+        xyzz_t s = load_xyzz(window_sums + w);
+        Co::add(cc, acc, s);
+    }
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_extra; i++) { xyzz_t s = load_xyzz(extra + (size_t)job * n_extra + i); Co::add(cc, acc, s); }
+    if (threadIdx.x == 0) {
+        if (out_partial) store_xyzz(out_partial + job, acc);
+        if (out_raw) store_xyzz(out_raw + job, acc);
+    }
+}
+
 // out[j] = sum_r partials[r * m + j], j < m: the G-way add after an all-gather of m shares per rank (rank-major, as the
 // gather leaves them).  One CTA per output, one thread (G <= 16 additions); the host normalises.
 template <int CURVE>

@@ -1,8 +1,8 @@
 """Development tool: where the end-to-end (host-scalar) MSM loses time against the device-resident one.
 
 For every setting of the segment knobs (ACCMSM_SEG_PCTS, cumulative boundaries in percent) it times accmsm_msm from a
-page-locked host buffer with and without the copies (ACCMSM_SKIP_H2D reuses the scalars of the previous call: timing only)
-and prints the library's segment timeline (ACCMSM_TRACE) of one call.  One process per setting (the knobs are read at init).
+page-locked host buffer against the device-resident MSM and prints the library's segment timeline (ACCMSM_TRACE) of one call.
+One process per setting (the knobs are read at init).
 
     python tools/e2e_segments.py            # sweep, one subprocess per setting
 """
@@ -58,11 +58,10 @@ def main():
         return
     settings = [s for s in (sys.argv[1:] or ["12", "25", "12,62", "10,45", "25,75", "6,30,70"])]
     for pcts in settings:
-        for skip in ("0", "1"):
-            env = dict(os.environ, ACCMSM_SEG_PCTS=pcts, ACCMSM_SKIP_H2D=skip)
-            r = subprocess.run([sys.executable, __file__, "--child", "20", "30"], env=env, capture_output=True, text=True)
-            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
-            print(f"pcts={pcts} skip_h2d={skip}: {line[-1] if line else r.stderr[-400:]}", flush=True)
+        env = dict(os.environ, ACCMSM_SEG_PCTS=pcts)
+        r = subprocess.run([sys.executable, __file__, "--child", "20", "30"], env=env, capture_output=True, text=True)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        print(f"pcts={pcts}: {line[-1] if line else r.stderr[-400:]}", flush=True)
         env = dict(os.environ, ACCMSM_SEG_PCTS=pcts, ACCMSM_TRACE="1")
         r = subprocess.run([sys.executable, __file__, "--child", "20", "1"], env=env, capture_output=True, text=True)
         tr = [l for l in r.stderr.splitlines() if "accmsm trace" in l]
