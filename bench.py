@@ -16,6 +16,7 @@ GPUs is a single N * 2^20-point MSM (config 5 of BASELINE.json sweeps 2^12 .. 2^
 from __future__ import annotations
 
 import argparse
+import shutil
 import json
 import os
 import statistics
@@ -182,7 +183,10 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
         "config": {"workload": f"pallas_msm_2^{LOG_N_PER_GPU}_per_gpu", "points_per_gpu": n_full, "curve": "pallas",
                    "note": "CPU restatement of ark-ec 0.2.0 VariableBaseMSM (c = ln-rule, rayon-over-windows -> OpenMP over windows); "
-                           "the Rust reference cannot be built in this image (no cargo)"},
+                           "the Rust reference cannot be built in this image (no cargo)",
+                   # probe, do not assume -- with a toolchain on the box `cargo run --release --features parallel --example
+                   # scaling-pc` of the reference would be the true arkworks number; none of the pool's boxes has one (no network either)
+                   "cargo_on_this_box": shutil.which("cargo") is not None},
         "cpu_baseline": {"value": round(mpts, 4), "unit": "Mpts/s", "cores": cores, "kind": "port",
                          "sample": f"one {n}-point MSM per step (the per-GPU share of the workload is 2^{LOG_N_PER_GPU} points), canonical scalars"},
         "e2e": {"value": round(mpts, 4), "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
