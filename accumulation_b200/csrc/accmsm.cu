@@ -2,6 +2,7 @@
 // declared in include/accmsm.h.  No CPU arithmetic path exists here: every group / field operation is a
 // CUDA kernel from msm.cuh / vec.cuh, and every entry point fails with ACCMSM_E_CUDA without a device.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -102,6 +103,7 @@ struct accmsm_ctx {
     bool no_coop_precompute = false;                            // development knob (ACCMSM_NO_COOP_PRECOMPUTE)
     bool trace = false;                                         // development knob ACCMSM_TRACE: timeline of the segments of a pipelined host-scalar MSM on stderr
     std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
+    std::vector<double> trace_host_us;                          // host clock at every trace point (when the launch was ENQUEUED)
     int sort_lb_override = 0;                                   // development knob (ACCMSM_SORT_LB), 0 = automatic; -1 = first-version sort
     DevBuf<uint8_t> oneshot_inf, ipa_tabs;      // ipa_tabs: half tables of h(X)'s coefficients (ipa_half_tables)
     bool no_ipa_tabs = false;                   // development knob (ACCMSM_NO_IPA_TABS)
@@ -187,14 +189,18 @@ void collect_timings(accmsm_ctx *ctx) {
         prev = i;
     }
     if (ctx->trace && !ctx->trace_ev.empty()) {      // ACCMSM_TRACE: timeline of the segments of a pipelined host-scalar MSM
+        size_t ti = 0;
         for (auto &le : ctx->trace_ev) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ctx->trace_ev[0].second, le.second) != cudaSuccess) (void)cudaGetLastError();
-            fprintf(stderr, "[accmsm trace] %8.3f ms  %s\n", ms, le.first.c_str());
+            const double host_ms = ti < ctx->trace_host_us.size() ? (ctx->trace_host_us[ti] - ctx->trace_host_us[0]) / 1e3 : 0.0;
+            ti++;
+            fprintf(stderr, "[accmsm trace] %8.3f ms (enqueued by the host at %7.3f ms)  %s\n", ms, host_ms, le.first.c_str());
             if (&le != &ctx->trace_ev[0]) cudaEventDestroy(le.second);
         }
         cudaEventDestroy(ctx->trace_ev[0].second);
         ctx->trace_ev.clear();
+        ctx->trace_host_us.clear();
     }
 }
 
@@ -202,6 +208,7 @@ void trace_point(accmsm_ctx *ctx, cudaStream_t st, const std::string &label) {
     if (!ctx->trace) return;
     cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st);
     ctx->trace_ev.push_back({label, ev});
+    ctx->trace_host_us.push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count());
 }
 
 // side stream (see accmsm_ctx::aux_stream): aux_begin makes it wait for everything enqueued on `st` so far and returns it
