@@ -20,7 +20,9 @@
  * synchronises its stream).  The ctx has one workspace; work left in flight by such a call is ordered before every later
  * call on any stream by an event, so interleaving streams is safe.  Small host arguments (challenges, randomizers) are
  * copied before the call returns: the caller may reuse its buffers immediately, page-locked or not.
- * There is no CPU fallback: without a CUDA device accmsm_init fails with ACCMSM_E_CUDA.
+ * There is no CPU fallback: without a CUDA device accmsm_init fails with ACCMSM_E_CUDA.  Two O(1) pieces of field arithmetic
+ * run on the calling host thread by design: the affine conversion (one inversion) of the un-normalised sums an entry point
+ * returns, and the inverse of an opening round's challenge -- never an MSM, a vector kernel or a point addition.
  * A ctx is bound to one GPU (accmsm_init) or to a group of GPUs of one box (accmsm_init_multi) and serialises its calls
  * internally.  Limits: a registered key has < 2^31 bases, and jobs x windows x n < 2^31 per MSM pass (n < 2^27 at the
  * automatic window sizes).
