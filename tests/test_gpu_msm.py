@@ -489,16 +489,17 @@ def test_experimental_batch_affine_rounds(monkeypatch):
         c2.close()
 
 
-@pytest.mark.parametrize("pinned", [False, True])
-def test_chunked_upload_overlapping_the_digit_kernel(ctx, pinned):
-    """Host scalar vectors of >= 16 MiB go up in 4 MiB chunks on a copy stream with the digit kernel following chunk by
-    chunk (msm_host_scalars); ragged last chunk, pageable (staged by several threads) and page-locked sources, result
-    bit-exact with the oracle and with the same MSM from device-resident scalars."""
+@pytest.mark.parametrize("curve,pinned", [(0, False), (0, True), (1, True)])
+def test_chunked_upload_overlapping_the_digit_kernel(ctx, curve, pinned):
+    """Host scalar vectors of >= 16 MiB go up in 4 MiB chunks on a copy stream, cut into two point segments that add into one
+    bucket set (msm_host_scalars: the second segment travels while the first is sorted and accumulated, fix-up on the side
+    stream); ragged last chunk, pageable (staged by several threads) and page-locked sources, both curves, result bit-exact
+    with the oracle and with the same MSM from device-resident scalars."""
     import torch
     n = (1 << 19) + 4097
-    key = ctx.register_synthetic_bases(0, 77, n)
+    key = ctx.register_synthetic_bases(curve, 77, n)
     key.precompute()
-    sc = cref.gen_scalars(cref.FQ, 78, n, True)
+    sc = cref.gen_scalars(cref.scalar_field(curve), 78, n, True)
     if pinned:
         buf = ab.pinned_array((n, 4))
         buf[:] = sc
@@ -511,7 +512,7 @@ def test_chunked_upload_overlapping_the_digit_kernel(ctx, pinned):
     dev = ctx.msm_dev(key, d_sc.data_ptr(), n)
     assert same_point(got, dev) and same_point(again, dev)
     pts = ctx.download_bases(key)
-    assert same_point(got, cref.commit(0, pts, sc))
+    assert same_point(got, cref.commit(curve, pts, sc))
     if pinned:
         ab.release_pinned(buf)
     key.release()
