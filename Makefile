@@ -3,7 +3,7 @@
 #   make oracle     -> oracle/liboracle.so            (test infrastructure)
 #   make harness    -> tests/host/as_tests            (C++ parity harness; needs both of the above)
 NVCC ?= /usr/local/cuda/bin/nvcc
-CXX  ?= /usr/bin/g++
+HOSTCXX ?= /usr/bin/g++   # not $$(CXX): build images export CXX to toolchains without libgomp
 CSRC := accumulation_b200/csrc
 DEPS := $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.inc) include/accmsm.h
 
@@ -17,7 +17,7 @@ oracle:
 	$(MAKE) -C oracle
 
 harness: accumulation_b200/libaccmsm.so oracle tests/host/as_tests.cpp accumulation_b200/host/ark_mirror.hpp
-	$(CXX) -O2 -std=c++17 -Wall -o tests/host/as_tests tests/host/as_tests.cpp -Laccumulation_b200 -Loracle \
+	$(HOSTCXX) -O2 -std=c++17 -Wall -o tests/host/as_tests tests/host/as_tests.cpp -Laccumulation_b200 -Loracle \
 	    -l:libaccmsm.so -l:liboracle.so -Wl,-rpath,$(CURDIR)/accumulation_b200 -Wl,-rpath,$(CURDIR)/oracle -fopenmp -pthread
 
 clean:

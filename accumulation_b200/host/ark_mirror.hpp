@@ -197,6 +197,63 @@ struct InnerProductArgPC {
         p.final_comm_key = affine_from(fk, 0);
         return p;
     }
+    // The same loop with ONE library call per round (accmsm_ipa_open_fold_round: fold with the challenge squeezed from the
+    // previous (l, r) -- its inverse is computed inside the library, on the host, like upstream's round_challenge.inverse() --
+    // and run the next round): what the patched open_individual_opening_challenges uses.  round_challenge(l, r) -> xi.
+    static IpaProofCore open_one_call_per_round(const CommitterKey &ck, const std::vector<Fe> &combined_coeffs, int log_d, const Fe &point,
+                                                const Affine &h_prime, const std::function<Fe(const Affine &, const Affine &)> &round_challenge,
+                                                const std::optional<Fe> &xi0 = std::nullopt) {
+        uint64_t hp[8]; affine_to(h_prime, hp);
+        uint64_t sess = 0;
+        if (xi0 && !ck.has_hiding()) throw AccmsmError("open: the key has no hiding generator");
+        ck.ctx()->check(accmsm_ipa_open_begin(ck.ctx()->raw(), ck.handle(), combined_coeffs.empty() ? nullptr : combined_coeffs[0].data(),
+                                              combined_coeffs.size(), log_d, point.data(), xi0 ? nullptr : hp, &sess), "ipa_open_begin");
+        if (xi0) ck.ctx()->check(accmsm_ipa_open_use_hiding_generator(ck.ctx()->raw(), sess, ck.hiding_index(), xi0->data()), "ipa_open_use_hiding_generator");
+        IpaProofCore p;
+        uint64_t l[8], rr[8]; uint8_t li = 0, ri = 0; int done = log_d == 0;
+        if (!done) ck.ctx()->check(accmsm_ipa_open_round(ck.ctx()->raw(), sess, l, &li, rr, &ri), "ipa_open_round");
+        while (!done) {
+            p.l_vec.push_back(affine_from(l, li)); p.r_vec.push_back(affine_from(rr, ri));
+            Fe xi = round_challenge(p.l_vec.back(), p.r_vec.back());
+            p.round_challenges.push_back(xi);
+            ck.ctx()->check(accmsm_ipa_open_fold_round(ck.ctx()->raw(), sess, xi.data(), l, &li, rr, &ri, &done), "ipa_open_fold_round");
+        }
+        uint64_t fk[8];
+        ck.ctx()->check(accmsm_ipa_open_finish(ck.ctx()->raw(), sess, fk, p.c.data()), "ipa_open_finish");
+        p.final_comm_key = affine_from(fk, 0);
+        return p;
+    }
+};
+
+// ark_ec::msm::VariableBaseMSM::multi_scalar_mul(&bases, &scalars).into_affine() on bases that are NOT a registered key: the short
+// linear combinations of commitments (src/hp_as/mod.rs:391-406, src/ipa_pc_as/mod.rs:322-343) and the 2k + 3 term group equation of
+// IpaPC::succinct_check (:198-205).  Scalars are BigInteger256 images (canonical, `into_repr()` done by the caller, as upstream).
+struct VariableBaseMSM {
+    static Affine multi_scalar_mul(const Context &ctx, int curve, const std::vector<Affine> &bases, const std::vector<Fe> &scalars_canonical) {
+        const size_t n = std::min(bases.size(), scalars_canonical.size());      // ark-ec truncates to the shorter slice
+        std::vector<uint64_t> xy(n * 8); std::vector<uint8_t> inf(n);
+        for (size_t i = 0; i < n; i++) { affine_to(bases[i], xy.data() + 8 * i); inf[i] = bases[i].infinity; }
+        uint64_t out[8]; uint8_t oi = 0;
+        ctx.check(accmsm_msm_oneshot(ctx.raw(), curve, xy.data(), inf.data(), n ? scalars_canonical[0].data() : nullptr, 0, n, out, &oi), "msm_oneshot");
+        return affine_from(out, oi);
+    }
+    // m such MSMs of equal length in shared passes (the succinct checks of all inputs and accumulators of one prove / verify)
+    static std::vector<Affine> multi_scalar_mul_batch(const Context &ctx, int curve, const std::vector<std::vector<Affine>> &bases,
+                                                      const std::vector<std::vector<Fe>> &scalars_canonical) {
+        const size_t m = std::min(bases.size(), scalars_canonical.size());
+        size_t n = m ? SIZE_MAX : 0;
+        for (size_t j = 0; j < m; j++) n = std::min(n, std::min(bases[j].size(), scalars_canonical[j].size()));
+        std::vector<uint64_t> xy(m * n * 8), sc(m * n * 4); std::vector<uint8_t> inf(m * n);
+        for (size_t j = 0; j < m; j++) for (size_t i = 0; i < n; i++) {
+            affine_to(bases[j][i], xy.data() + 8 * (j * n + i)); inf[j * n + i] = bases[j][i].infinity;
+            std::copy(scalars_canonical[j][i].begin(), scalars_canonical[j][i].end(), sc.begin() + 4 * (j * n + i));
+        }
+        std::vector<uint64_t> out(m * 8); std::vector<uint8_t> oi(m);
+        ctx.check(accmsm_msm_oneshot_batch(ctx.raw(), curve, xy.data(), inf.data(), sc.data(), 0, n, m, out.data(), oi.data()), "msm_oneshot_batch");
+        std::vector<Affine> res(m);
+        for (size_t j = 0; j < m; j++) res[j] = affine_from(out.data() + 8 * j, oi[j]);
+        return res;
+    }
 };
 
 struct ASForHadamardProducts {

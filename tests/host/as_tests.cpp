@@ -128,10 +128,31 @@ int main() {
             CHECK((tag + "ipa open: h' as a point == h' as (hiding index, xi_0)").c_str(),
                   p1.l_vec == p2.l_vec && p1.r_vec == p2.r_vec && p1.final_comm_key == p2.final_comm_key && p1.c == p2.c);
         }
+        {   // one library call per round (accmsm_ipa_open_fold_round, the challenge's inverse taken inside the library): same proof
+            IpaProofCore p3 = InnerProductArgPC::open_one_call_per_round(ipa_ck, coeffs, k, z, hgen, [&](const Affine &l, const Affine &r) { return squeeze(l, r).first; });
+            CHECK((tag + "ipa open: one call per round (fold_round) gives the same proof").c_str(),
+                  p3.l_vec == proof.l_vec && p3.r_vec == proof.r_vec && p3.final_comm_key == proof.final_comm_key && p3.c == proof.c &&
+                  p3.round_challenges == proof.round_challenges);
+        }
+        {   // VariableBaseMSM::multi_scalar_mul on unregistered bases (2k + 3 = 19 terms), alone and three of them in one batched call
+            const size_t nt = 2 * k + 3;
+            std::vector<std::vector<Affine>> bb(3); std::vector<std::vector<Fe>> ss(3); std::vector<Affine> expd(3);
+            for (int j = 0; j < 3; j++) {
+                bb[j].assign(gens.begin() + 100 * j, gens.begin() + 100 * j + nt);
+                auto m = gen_scalars(sf, 700 + j, nt); ss[j].resize(nt);
+                oracle_fe_from_mont(sf, m[0].data(), ss[j][0].data(), nt);
+                if (j == 1) { ss[j][0] = Fe{0, 0, 0, 0}; ss[j][1] = Fe{1, 0, 0, 0}; bb[j][nt - 1] = bb[j][0]; }      // zero, one, a repeated base
+                auto xy = flat(bb[j]); uint64_t o[8]; uint8_t oi = 0;
+                oracle_msm_ark(curve, xy.data(), nullptr, nt, ss[j][0].data(), nt, o, &oi);
+                expd[j] = affine_from(o, oi);
+            }
+            CHECK((tag + "multi_scalar_mul on unregistered bases").c_str(), VariableBaseMSM::multi_scalar_mul(*ctx, curve, bb[1], ss[1]) == expd[1]);
+            CHECK((tag + "three one-shot MSMs in one batched call").c_str(), VariableBaseMSM::multi_scalar_mul_batch(*ctx, curve, bb, ss) == expd);
+        }
         {   // the materialised folded key (accmsm_set_ipa_fold) changes nothing in the proof: forced every 2 rounds here
             ctx->check(accmsm_set_ipa_fold(ctx->raw(), 2, 2), "set_ipa_fold");
             IpaProofCore pf = InnerProductArgPC::open(ipa_ck, coeffs, k, z, hgen, squeeze);
-            ctx->check(accmsm_set_ipa_fold(ctx->raw(), 5, 14), "set_ipa_fold");
+            ctx->check(accmsm_set_ipa_fold(ctx->raw(), 5, 11), "set_ipa_fold");
             CHECK((tag + "ipa open: same proof with the folded key materialised every 2 rounds").c_str(),
                   pf.l_vec == proof.l_vec && pf.r_vec == proof.r_vec && pf.final_comm_key == proof.final_comm_key && pf.c == proof.c);
         }

@@ -41,4 +41,4 @@ def test_cpp_harness_scenarios(devices):
     p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, ACCMSM_TEST_DEVICES=devices))
     print(p.stdout[-4000:])
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
-    assert "FAIL" not in p.stdout and p.stdout.count("PASS") >= 40
+    assert "FAIL" not in p.stdout and p.stdout.count("PASS") >= 52
