@@ -1472,6 +1472,8 @@ static int ipa_half_tables(accmsm_ctx *ctx, int sfield, const uint8_t *d_challen
     if (k < 8 || k > 30 || ctx->no_ipa_tabs) return ACCMSM_OK;
     const uint32_t kl = (uint32_t)k / 2u, entries = (1u << kl) + (1u << ((uint32_t)k - kl));
     if (n < 4 * (size_t)entries) return ACCMSM_OK;
+    // the tables are workspace: an earlier call left in flight on another stream may still be reading them
+    { int wrc = ws_acquire(ctx, st); if (wrc) return wrc; }
     CU(ctx, ctx->ipa_tabs.ensure((size_t)entries * 32));
     if (sfield == 0) k_ipa_half_tables<0><<<(entries + 255) / 256, 256, 0, st>>>(d_challenges, k, ctx->ipa_tabs.p);
     else k_ipa_half_tables<1><<<(entries + 255) / 256, 256, 0, st>>>(d_challenges, k, ctx->ipa_tabs.p);
